@@ -175,6 +175,10 @@ int lulesh_b200_download(lulesh_b200 *h, int field, double *dst, size_t count);
 int lulesh_b200_upload(lulesh_b200 *h, int field, const double *src, size_t count);
 size_t lulesh_b200_field_count(lulesh_b200 *h, int field);
 
+/* When on, run/step also store the fx..fz / xdd..zdd mirrors and ql/qq, which
+ * the fused kernels otherwise keep in registers (tests, -v style dumps). */
+int lulesh_b200_set_debug(lulesh_b200 *h, int on);
+
 /* Per-kernel entry points (unit tests, ncu).  Each runs synchronously on the
  * handle's stream and returns the sticky error word.
  *   force     : K1  InitStressTerms + IntegrateStress + HourglassControl +

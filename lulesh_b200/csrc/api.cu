@@ -1,0 +1,902 @@
+// C ABI + runtime of the B200-native Lagrange-leapfrog step: device mirror of
+// the reference Domain (lulesh.h:148-595) in HBM, the per-cycle launch sequence
+// (CUDA graph at one rank; compute + comm streams with NCCL halo exchange at
+// several ranks) and the host-side construction of the device layouts.
+//
+// There is no CPU fallback anywhere in this file: without a usable sm_100
+// device every compute entry point returns LULESH_B200_ECUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only; every NCCL symbol is resolved with dlsym at run time
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lulesh_b200.h"
+#include "kernels.cuh"
+
+using namespace lb200;
+
+// --------------------------------------------------------------------------
+// error plumbing
+// --------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...)
+{
+   char buf[512];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof buf, fmt, ap);
+   va_end(ap);
+   g_last_error = buf;
+   return code;
+}
+
+#define CK(call)                                                                      \
+   do {                                                                               \
+      cudaError_t e_ = (call);                                                        \
+      if (e_ != cudaSuccess)                                                          \
+         return fail(LULESH_B200_ECUDA, "%s failed: %s (%s:%d)", #call,               \
+                     cudaGetErrorString(e_), __FILE__, __LINE__);                     \
+   } while (0)
+
+// --------------------------------------------------------------------------
+// NCCL, loaded lazily so that single-GPU use has no NCCL dependency.  In a
+// python process that already imported torch the dlopen returns torch's copy.
+// --------------------------------------------------------------------------
+struct NcclApi {
+   void *lib = nullptr;
+   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+   ncclResult_t (*GroupStart)() = nullptr;
+   ncclResult_t (*GroupEnd)() = nullptr;
+   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                             cudaStream_t) = nullptr;
+   const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi *nccl_api()
+{
+   static NcclApi api;
+   static bool tried = false;
+   if (tried) return api.lib ? &api : nullptr;
+   tried = true;
+   const char *names[] = {"libnccl.so.2", "libnccl.so"};
+   for (const char *n : names)
+      if ((api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+   if (!api.lib) return nullptr;
+#define SYM(field, name)                                                      \
+   *(void **)(&api.field) = dlsym(api.lib, name);                             \
+   if (!api.field) { api.lib = nullptr; return nullptr; }
+   SYM(GetUniqueId, "ncclGetUniqueId")
+   SYM(CommInitRank, "ncclCommInitRank")
+   SYM(CommDestroy, "ncclCommDestroy")
+   SYM(GroupStart, "ncclGroupStart")
+   SYM(GroupEnd, "ncclGroupEnd")
+   SYM(Send, "ncclSend")
+   SYM(Recv, "ncclRecv")
+   SYM(AllReduce, "ncclAllReduce")
+   SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+   return &api;
+}
+
+#define NK(call)                                                                      \
+   do {                                                                               \
+      ncclResult_t r_ = (call);                                                       \
+      if (r_ != ncclSuccess)                                                          \
+         return fail(LULESH_B200_ENCCL, "%s failed: %s", #call,                       \
+                     h->nccl->GetErrorString(r_));                                    \
+   } while (0)
+
+// --------------------------------------------------------------------------
+// handle
+// --------------------------------------------------------------------------
+struct Message {      // one neighbour of the node-halo exchange
+   int rank, count;   // nodes shared with that neighbour
+   size_t send_off, recv_off;   // doubles, into sendbuf / fhalo (3 fields each)
+};
+
+struct FaceMessage {  // one face neighbour of the MonoQ exchange
+   int rank, count;
+   size_t send_off;   // into mq_send (3 fields)
+   size_t ghost_off;  // element offset of the ghost block inside delv_*
+};
+
+struct lulesh_b200 {
+   int device = 0;
+   int numRanks = 1, rank = 0;
+   cudaStream_t stream = nullptr, comm_stream = nullptr;
+   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+   KParams P{};
+   Ctl *h_ctl = nullptr;   // pinned mirror
+   std::vector<void *> allocs;
+   size_t device_bytes = 0, upload_bytes = 0;
+   double *field_ptr[LULESH_F_COUNT] = {};
+   size_t field_cnt[LULESH_F_COUNT] = {};
+   int debug = 0;
+   // graph of one cycle (single rank)
+   cudaGraphExec_t graph = nullptr;
+   int graph_debug = -1;
+   // comm
+   NcclApi *nccl = nullptr;
+   ncclComm_t comm = nullptr;
+   std::vector<Message> msgs;
+   std::vector<FaceMessage> faces;
+   double *sendbuf = nullptr;
+   int *pack_idx = nullptr;
+   size_t send_total = 0;
+   double *mq_send = nullptr;
+   int *mq_idx = nullptr;
+   size_t mq_total = 0;
+   int64_t launches = 0;
+};
+
+template <typename T>
+static int dev_alloc(lulesh_b200 *h, T **out, size_t count)
+{
+   void *p = nullptr;
+   const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+   CK(cudaMalloc(&p, bytes));
+   h->allocs.push_back(p);
+   h->device_bytes += bytes;
+   *out = static_cast<T *>(p);
+   return 0;
+}
+
+template <typename T>
+static int dev_upload(lulesh_b200 *h, T **out, const T *src, size_t count)
+{
+   int rc = dev_alloc(h, out, count);
+   if (rc) return rc;
+   if (count) {
+      CK(cudaMemcpy(*out, src, count * sizeof(T), cudaMemcpyHostToDevice));
+      h->upload_bytes += count * sizeof(T);
+   }
+   return 0;
+}
+
+template <typename T>
+static int dev_zero(lulesh_b200 *h, T **out, size_t count)
+{
+   int rc = dev_alloc(h, out, count);
+   if (rc) return rc;
+   CK(cudaMemset(*out, 0, std::max<size_t>(count, 1) * sizeof(T)));
+   return 0;
+}
+
+static int region_rep(int r, int numReg, int cost)   // lulesh.cc:2393-2400
+{
+   if (r < numReg / 2) return 1;
+   if (r < numReg - (numReg + 15) / 20) return 1 + cost;
+   return 10 * (1 + cost);
+}
+
+// the 26 neighbour directions (dcol, drow, dplane): 6 faces in the ghost-block
+// order of lulesh-init.cc:582-610, then 12 edges, then 8 corners
+static const int k_dirs[26][3] = {
+   {0, 0, -1}, {0, 0, 1}, {0, -1, 0}, {0, 1, 0}, {-1, 0, 0}, {1, 0, 0},
+   {-1, -1, 0}, {0, -1, -1}, {-1, 0, -1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1},
+   {-1, 1, 0}, {0, -1, 1}, {-1, 0, 1}, {1, -1, 0}, {0, 1, -1}, {1, 0, -1},
+   {-1, -1, -1}, {-1, -1, 1}, {1, -1, -1}, {1, -1, 1},
+   {-1, 1, -1}, {-1, 1, 1}, {1, 1, -1}, {1, 1, 1}};
+
+static int neighbour_rank(const lulesh_b200_host_view *v, const int dir[3])
+{
+   const int c = v->colLoc + dir[0], r = v->rowLoc + dir[1], p = v->planeLoc + dir[2];
+   if (c < 0 || c >= v->px || r < 0 || r >= v->py || p < 0 || p >= v->pz) return -1;
+   return p * v->px * v->py + r * v->px + c;
+}
+
+static void shared_nodes(const lulesh_b200_host_view *v, const int dir[3], std::vector<int> &out)
+{
+   const int nx1 = v->sizeX + 1, ny1 = v->sizeY + 1, nz1 = v->sizeZ + 1;
+   const int i0 = dir[0] > 0 ? v->sizeX : 0, i1 = dir[0] == 0 ? nx1 : i0 + 1;
+   const int j0 = dir[1] > 0 ? v->sizeY : 0, j1 = dir[1] == 0 ? ny1 : j0 + 1;
+   const int k0 = dir[2] > 0 ? v->sizeZ : 0, k1 = dir[2] == 0 ? nz1 : k0 + 1;
+   out.clear();
+   for (int k = k0; k < k1; ++k)
+      for (int j = j0; j < j1; ++j)
+         for (int i = i0; i < i1; ++i) out.push_back(k * nx1 * ny1 + j * nx1 + i);
+}
+
+// boundary element layer facing `dir` (a face direction), in the (slow,fast)
+// order the ghost indices of lulesh-init.cc:613-671 expect
+static void face_elems(const lulesh_b200_host_view *v, const int dir[3], std::vector<int> &out)
+{
+   const int sx = v->sizeX, sy = v->sizeY, sz = v->sizeZ;
+   out.clear();
+   if (dir[2] != 0) {
+      const int k = dir[2] < 0 ? 0 : sz - 1;
+      for (int j = 0; j < sy; ++j) for (int i = 0; i < sx; ++i) out.push_back(k * sx * sy + j * sx + i);
+   } else if (dir[1] != 0) {
+      const int j = dir[1] < 0 ? 0 : sy - 1;
+      for (int k = 0; k < sz; ++k) for (int i = 0; i < sx; ++i) out.push_back(k * sx * sy + j * sx + i);
+   } else {
+      const int i = dir[0] < 0 ? 0 : sx - 1;
+      for (int k = 0; k < sz; ++k) for (int j = 0; j < sy; ++j) out.push_back(k * sx * sy + j * sx + i);
+   }
+}
+
+// --------------------------------------------------------------------------
+// create / destroy
+// --------------------------------------------------------------------------
+extern "C" const char *lulesh_b200_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int lulesh_b200_get_unique_id(void *out_id)
+{
+   NcclApi *api = nccl_api();
+   if (!api) return fail(LULESH_B200_ENCCL, "libnccl.so.2 could not be loaded");
+   static_assert(sizeof(ncclUniqueId) == LULESH_B200_UNIQUE_ID_BYTES, "unique id size");
+   ncclUniqueId id;
+   ncclResult_t r = api->GetUniqueId(&id);
+   if (r != ncclSuccess) return fail(LULESH_B200_ENCCL, "ncclGetUniqueId: %s", api->GetErrorString(r));
+   memcpy(out_id, &id, sizeof id);
+   return 0;
+}
+
+static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void *unique_id,
+                      std::vector<unsigned char> &nodeFlags);
+
+static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int device,
+                       const void *unique_id)
+{
+   if (v->abi_version != LULESH_B200_ABI_VERSION)
+      return fail(LULESH_B200_EINVAL, "abi_version %d != %d", v->abi_version, LULESH_B200_ABI_VERSION);
+   const int ne = v->numElem, nn = v->numNode;
+   if (ne <= 0 || nn <= 0 || (long long)v->sizeX * v->sizeY * v->sizeZ != ne ||
+       (long long)(v->sizeX + 1) * (v->sizeY + 1) * (v->sizeZ + 1) != nn)
+      return fail(LULESH_B200_EINVAL, "inconsistent sizes in host view");
+   if (v->numRanks < 1 || v->px * v->py * v->pz != v->numRanks || v->rank < 0 || v->rank >= v->numRanks)
+      return fail(LULESH_B200_EINVAL, "inconsistent decomposition in host view");
+   if (!v->x || !v->nodelist || !v->nodeElemStart || !v->nodeElemCornerList || !v->regElemSize ||
+       !v->regElemlist || v->numReg < 1)
+      return fail(LULESH_B200_EINVAL, "null array in host view");
+
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      return fail(LULESH_B200_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+   if (device < 0 || device >= ndev) return fail(LULESH_B200_EINVAL, "device %d out of range", device);
+   cudaDeviceProp prop;
+   CK(cudaGetDeviceProperties(&prop, device));
+   if (prop.major != 10)
+      return fail(LULESH_B200_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                  device, prop.major, prop.minor);
+   CK(cudaSetDevice(device));
+   h->device = device;
+   h->numRanks = v->numRanks;
+   h->rank = v->rank;
+   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+   CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+   CK(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
+   CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+   CK(cudaEventCreate(&h->ev_t0));
+   CK(cudaEventCreate(&h->ev_t1));
+   CK(cudaMallocHost(&h->h_ctl, sizeof(Ctl)));
+
+   KParams &P = h->P;
+   P.ne = ne; P.nn = nn;
+   P.allElem = ne + 2 * v->sizeX * v->sizeY + 2 * v->sizeX * v->sizeZ + 2 * v->sizeY * v->sizeZ;
+   P.ne_pad = (ne + 15) & ~15;
+   P.nn_pad = (nn + 31) & ~31;
+   P.c = v->constants;
+   int rc;
+
+   // ---- control block
+   Ctl c0{};
+   c0.dtcourant_bits = 0; c0.dthydro_bits = 0;
+   memcpy(&c0.dtcourant_bits, &v->scalars.dtcourant, 8);
+   memcpy(&c0.dthydro_bits, &v->scalars.dthydro, 8);
+   c0.dtfixed = v->scalars.dtfixed; c0.time = v->scalars.time; c0.deltatime = v->scalars.deltatime;
+   c0.deltatimemultlb = v->scalars.deltatimemultlb; c0.deltatimemultub = v->scalars.deltatimemultub;
+   c0.dtmax = v->scalars.dtmax; c0.stoptime = v->scalars.stoptime;
+   c0.gnewdt = 1.0e+20; c0.cycle = v->scalars.cycle; c0.max_cycles = INT_MAX; c0.done = 0; c0.error = 0;
+   if ((rc = dev_upload(h, &P.ctl, &c0, 1))) return rc;
+
+   // ---- node-centred state
+#define UP_NODE(name, id)                                                               \
+   { double *p_; if ((rc = dev_upload(h, &p_, v->name, (size_t)nn))) return rc;         \
+     h->field_ptr[id] = p_; h->field_cnt[id] = nn; }
+   UP_NODE(x, LULESH_F_X) UP_NODE(y, LULESH_F_Y) UP_NODE(z, LULESH_F_Z)
+   UP_NODE(xd, LULESH_F_XD) UP_NODE(yd, LULESH_F_YD) UP_NODE(zd, LULESH_F_ZD)
+   UP_NODE(nodalMass, LULESH_F_NODALMASS)
+#undef UP_NODE
+   P.x = h->field_ptr[LULESH_F_X]; P.y = h->field_ptr[LULESH_F_Y]; P.z = h->field_ptr[LULESH_F_Z];
+   P.xd = h->field_ptr[LULESH_F_XD]; P.yd = h->field_ptr[LULESH_F_YD]; P.zd = h->field_ptr[LULESH_F_ZD];
+   P.nodalMass = h->field_ptr[LULESH_F_NODALMASS];
+   if ((rc = dev_zero(h, &P.dbg_f, (size_t)3 * nn))) return rc;
+   if ((rc = dev_zero(h, &P.dbg_a, (size_t)3 * nn))) return rc;
+   for (int a = 0; a < 3; ++a) {
+      h->field_ptr[LULESH_F_FX + a] = P.dbg_f + (size_t)a * nn; h->field_cnt[LULESH_F_FX + a] = nn;
+      h->field_ptr[LULESH_F_XDD + a] = P.dbg_a + (size_t)a * nn; h->field_cnt[LULESH_F_XDD + a] = nn;
+   }
+
+   // ---- element-centred state
+#define UP_ELEM(name, id, dst)                                                          \
+   { double *p_; if ((rc = dev_upload(h, &p_, v->name, (size_t)ne))) return rc;         \
+     h->field_ptr[id] = p_; h->field_cnt[id] = ne; dst = p_; }
+   UP_ELEM(e, LULESH_F_E, P.e) UP_ELEM(p, LULESH_F_P, P.p) UP_ELEM(q, LULESH_F_Q, P.q)
+   UP_ELEM(v, LULESH_F_V, P.v) UP_ELEM(ss, LULESH_F_SS, P.ss)
+   { double *p_; if ((rc = dev_upload(h, &p_, v->volo, (size_t)ne))) return rc;
+     h->field_ptr[LULESH_F_VOLO] = p_; h->field_cnt[LULESH_F_VOLO] = ne; P.volo = p_; }
+   { double *p_; if ((rc = dev_upload(h, &p_, v->elemMass, (size_t)ne))) return rc;
+     h->field_ptr[LULESH_F_ELEMMASS] = p_; h->field_cnt[LULESH_F_ELEMMASS] = ne; P.elemMass = p_; }
+#undef UP_ELEM
+#define ZERO_ELEM(id, dst, cnt)                                                         \
+   { double *p_; if ((rc = dev_zero(h, &p_, (size_t)(cnt)))) return rc;                 \
+     h->field_ptr[id] = p_; h->field_cnt[id] = (cnt); dst = p_; }
+   ZERO_ELEM(LULESH_F_QL, P.ql, ne) ZERO_ELEM(LULESH_F_QQ, P.qq, ne)
+   ZERO_ELEM(LULESH_F_VNEW, P.vnew, ne) ZERO_ELEM(LULESH_F_DELV, P.delv, ne)
+   ZERO_ELEM(LULESH_F_VDOV, P.vdov, ne) ZERO_ELEM(LULESH_F_AREALG, P.arealg, ne)
+   ZERO_ELEM(LULESH_F_DELX_XI, P.delx_xi, ne) ZERO_ELEM(LULESH_F_DELX_ETA, P.delx_eta, ne)
+   ZERO_ELEM(LULESH_F_DELX_ZETA, P.delx_zeta, ne)
+#undef ZERO_ELEM
+   {  // delv_xi/eta/zeta share one allocation [3][allElem] (ghost blocks at the tail of each)
+      double *g;
+      if ((rc = dev_zero(h, &g, (size_t)3 * P.allElem))) return rc;
+      P.delv_xi = g; P.delv_eta = g + P.allElem; P.delv_zeta = g + 2 * (size_t)P.allElem;
+      for (int a = 0; a < 3; ++a) {
+         h->field_ptr[LULESH_F_DELV_XI + a] = g + (size_t)a * P.allElem;
+         h->field_cnt[LULESH_F_DELV_XI + a] = P.allElem;
+      }
+   }
+   {
+      int *p_;
+#define UP_INT(name, cnt) if ((rc = dev_upload(h, &p_, v->name, (size_t)(cnt)))) return rc; P.name = p_;
+      UP_INT(nodelist, 8 * (size_t)ne)
+      UP_INT(lxim, ne) UP_INT(lxip, ne) UP_INT(letam, ne) UP_INT(letap, ne)
+      UP_INT(lzetam, ne) UP_INT(lzetap, ne) UP_INT(elemBC, ne)
+#undef UP_INT
+   }
+   if ((rc = dev_zero(h, &P.fcorner, (size_t)24 * P.ne_pad))) return rc;
+
+   // ---- corner gather table: CSR (lulesh-init.cc:295-319) -> 8-slot ELL, slot
+   // order == CSR order == ascending element; entries re-based to the SoA planes
+   {
+      std::vector<int> ell((size_t)8 * P.nn_pad, -1);
+      for (int n = 0; n < nn; ++n) {
+         const int b = v->nodeElemStart[n], e = v->nodeElemStart[n + 1];
+         if (e - b > 8 || e < b) return fail(LULESH_B200_EINVAL, "node %d has %d corners", n, e - b);
+         for (int k = b; k < e; ++k) {
+            const int ci = v->nodeElemCornerList[k];
+            if (ci < 0 || ci >= 8 * ne) return fail(LULESH_B200_EINVAL, "corner list entry out of range");
+            ell[(size_t)(k - b) * P.nn_pad + n] = (ci & 7) * P.ne_pad + (ci >> 3);
+         }
+      }
+      int *p_;
+      if ((rc = dev_upload(h, &p_, ell.data(), ell.size()))) return rc;
+      P.cornerEll = p_;
+   }
+
+   // ---- per-node flags from the symmetry node sets (lulesh-init.cc:514-533)
+   std::vector<unsigned char> nodeFlags(nn, 0);
+   for (int i = 0; i < v->numSymmX; ++i) nodeFlags[v->symmX[i]] |= NODE_SYMM_X;
+   for (int i = 0; i < v->numSymmY; ++i) nodeFlags[v->symmY[i]] |= NODE_SYMM_Y;
+   for (int i = 0; i < v->numSymmZ; ++i) nodeFlags[v->symmZ[i]] |= NODE_SYMM_Z;
+
+   // ---- region work list: regions ordered by descending rep (heaviest blocks are
+   // scheduled first), each padded to whole blocks so rep is block-uniform
+   {
+      std::vector<int> order(v->numReg);
+      for (int r = 0; r < v->numReg; ++r) order[r] = r;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+         return region_rep(a, v->numReg, v->cost) > region_rep(b, v->numReg, v->cost);
+      });
+      std::vector<int> work, reps;
+      long long total = 0;
+      for (int r : order) {
+         const int n = v->regElemSize[r];
+         total += n;
+         for (int t = 0; t < n; ++t) {
+            const int el = v->regElemlist[r][t];
+            if (el < 0 || el >= ne) return fail(LULESH_B200_EINVAL, "region list entry out of range");
+            work.push_back(el);
+         }
+         while (work.size() % MAT_THREADS) work.push_back(-1);
+         reps.resize(work.size() / MAT_THREADS, region_rep(r, v->numReg, v->cost));
+      }
+      if (total != ne) return fail(LULESH_B200_EINVAL, "region lists cover %lld of %d elements", total, ne);
+      int *p_;
+      if ((rc = dev_upload(h, &p_, work.data(), work.size()))) return rc;
+      P.workElem = p_;
+      if ((rc = dev_upload(h, &p_, reps.data(), reps.size()))) return rc;
+      P.workBlockRep = p_;
+      P.numWorkBlocks = (int)reps.size();
+   }
+
+   if (v->numRanks > 1) {
+      if ((rc = build_comm(h, v, unique_id, nodeFlags))) return rc;
+   }
+   {
+      unsigned char *p_;
+      if ((rc = dev_upload(h, &p_, nodeFlags.data(), nodeFlags.size()))) return rc;
+      P.nodeFlags = p_;
+   }
+   CK(cudaDeviceSynchronize());
+   return 0;
+}
+
+static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void *unique_id,
+                      std::vector<unsigned char> &nodeFlags)
+{
+   KParams &P = h->P;
+   int rc;
+   if (!unique_id) return fail(LULESH_B200_EINVAL, "numRanks > 1 needs an NCCL unique id");
+   h->nccl = nccl_api();
+   if (!h->nccl) return fail(LULESH_B200_ENCCL, "libnccl.so.2 could not be loaded");
+
+   // ---- node halo: boundary-node numbering, messages, canonical contribution lists
+   const int nn = v->numNode;
+   std::vector<int> bmap(nn, -1), nodes;
+   struct Dir { int q, rank; std::vector<int> nodes; };
+   std::vector<Dir> dirs;
+   for (int q = 0; q < 26; ++q) {
+      const int nb = neighbour_rank(v, k_dirs[q]);
+      if (nb < 0) continue;
+      Dir d{q, nb, {}};
+      shared_nodes(v, k_dirs[q], d.nodes);
+      for (int n : d.nodes) bmap[n] = 0;
+      dirs.push_back(std::move(d));
+   }
+   std::vector<int> bnode;
+   for (int n = 0; n < nn; ++n)
+      if (bmap[n] == 0) { bmap[n] = (int)bnode.size(); bnode.push_back(n); nodeFlags[n] |= NODE_COMM; }
+   const int nb = (int)bnode.size();
+   P.nbnode = nb;
+
+   size_t send_off = 0, recv_off = (size_t)3 * nb;
+   std::vector<int> pack_idx;
+   struct Contribution { int rank, base, stride; };
+   std::vector<std::vector<Contribution>> contrib(nb);
+   for (int b = 0; b < nb; ++b) contrib[b].push_back({v->rank, b, nb});
+   for (const Dir &d : dirs) {
+      Message m{d.rank, (int)d.nodes.size(), send_off, recv_off};
+      for (int a = 0; a < 3; ++a)
+         for (int t = 0; t < m.count; ++t) pack_idx.push_back(a * nb + bmap[d.nodes[t]]);
+      for (int t = 0; t < m.count; ++t)
+         contrib[bmap[d.nodes[t]]].push_back({d.rank, (int)(recv_off + t), m.count});
+      send_off += (size_t)3 * m.count;
+      recv_off += (size_t)3 * m.count;
+      h->msgs.push_back(m);
+   }
+   if (recv_off > (size_t)INT_MAX) return fail(LULESH_B200_EINVAL, "halo too large");
+   h->send_total = send_off;
+   P.fhalo_stride = (int)recv_off;
+   std::vector<int> bsum_start(nb + 1, 0), bsum_src;
+   for (int b = 0; b < nb; ++b) {
+      std::stable_sort(contrib[b].begin(), contrib[b].end(),
+                       [](const Contribution &x, const Contribution &y) { return x.rank < y.rank; });
+      for (const Contribution &c : contrib[b]) { bsum_src.push_back(c.base); bsum_src.push_back(c.stride); }
+      bsum_start[b + 1] = (int)(bsum_src.size() / 2);
+   }
+   int *pi;
+   if ((rc = dev_upload(h, &pi, bnode.data(), bnode.size()))) return rc;
+   P.bnode = pi;
+   if ((rc = dev_upload(h, &pi, bsum_start.data(), bsum_start.size()))) return rc;
+   P.bsum_start = pi;
+   if ((rc = dev_upload(h, &pi, bsum_src.data(), bsum_src.size()))) return rc;
+   P.bsum_src = pi;
+   if ((rc = dev_upload(h, &h->pack_idx, pack_idx.data(), pack_idx.size()))) return rc;
+   if ((rc = dev_zero(h, &P.fhalo, recv_off))) return rc;
+   if ((rc = dev_zero(h, &h->sendbuf, send_off))) return rc;
+
+   // ---- MonoQ: face neighbours only; ghost blocks in pMin,pMax,rMin,rMax,cMin,cMax order
+   size_t mq_off = 0, ghost = (size_t)v->numElem;
+   std::vector<int> mq_idx, elems;
+   for (int q = 0; q < 6; ++q) {
+      const int nbr = neighbour_rank(v, k_dirs[q]);
+      if (nbr < 0) continue;
+      face_elems(v, k_dirs[q], elems);
+      FaceMessage f{nbr, (int)elems.size(), mq_off, ghost};
+      for (int a = 0; a < 3; ++a)
+         for (int e : elems) mq_idx.push_back(a * P.allElem + e);
+      mq_off += (size_t)3 * f.count;
+      ghost += f.count;
+      h->faces.push_back(f);
+   }
+   h->mq_total = mq_off;
+   if ((rc = dev_upload(h, &h->mq_idx, mq_idx.data(), mq_idx.size()))) return rc;
+   if ((rc = dev_zero(h, &h->mq_send, mq_off))) return rc;
+
+   ncclUniqueId id;
+   memcpy(&id, unique_id, sizeof id);
+   NK(h->nccl->CommInitRank(&h->comm, v->numRanks, id, v->rank));
+   return 0;
+}
+
+extern "C" int lulesh_b200_create(const lulesh_b200_host_view *view, int device,
+                                  const void *unique_id, lulesh_b200 **out)
+{
+   if (!view || !out) return fail(LULESH_B200_EINVAL, "null argument");
+   *out = nullptr;
+   lulesh_b200 *h = new lulesh_b200();
+   const int rc = create_impl(h, view, device, unique_id);
+   if (rc) { lulesh_b200_destroy(h); return rc; }
+   *out = h;
+   return 0;
+}
+
+extern "C" void lulesh_b200_destroy(lulesh_b200 *h)
+{
+   if (!h) return;
+   cudaSetDevice(h->device);
+   if (h->stream) cudaStreamSynchronize(h->stream);
+   if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
+   if (h->graph) cudaGraphExecDestroy(h->graph);
+   for (void *p : h->allocs) cudaFree(p);
+   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+   if (h->ev_a) cudaEventDestroy(h->ev_a);
+   if (h->ev_b) cudaEventDestroy(h->ev_b);
+   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+   if (h->stream) cudaStreamDestroy(h->stream);
+   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+   delete h;
+}
+
+// --------------------------------------------------------------------------
+// the cycle
+// --------------------------------------------------------------------------
+static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
+
+// node-halo exchange of the three force planes (or the replicated mass)
+static int exchange_nodes(lulesh_b200 *h)
+{
+   const KParams &P = h->P;
+   k_gather_index<<<blocks_for((int)h->send_total, 256), 256, 0, h->stream>>>(
+      h->sendbuf, P.fhalo, h->pack_idx, (int)h->send_total);
+   CK(cudaEventRecord(h->ev_a, h->stream));
+   CK(cudaStreamWaitEvent(h->comm_stream, h->ev_a, 0));
+   NK(h->nccl->GroupStart());
+   for (const Message &m : h->msgs) {
+      NK(h->nccl->Recv(P.fhalo + m.recv_off, (size_t)3 * m.count, ncclDouble, m.rank, h->comm, h->comm_stream));
+      NK(h->nccl->Send(h->sendbuf + m.send_off, (size_t)3 * m.count, ncclDouble, m.rank, h->comm, h->comm_stream));
+   }
+   NK(h->nccl->GroupEnd());
+   CK(cudaEventRecord(h->ev_b, h->comm_stream));
+   h->launches += 1;
+   return 0;
+}
+
+static int exchange_monoq(lulesh_b200 *h)
+{
+   const KParams &P = h->P;
+   k_gather_index<<<blocks_for((int)h->mq_total, 256), 256, 0, h->stream>>>(
+      h->mq_send, P.delv_xi, h->mq_idx, (int)h->mq_total);
+   CK(cudaEventRecord(h->ev_a, h->stream));
+   CK(cudaStreamWaitEvent(h->comm_stream, h->ev_a, 0));
+   NK(h->nccl->GroupStart());
+   for (const FaceMessage &f : h->faces)
+      for (int a = 0; a < 3; ++a) {   // receive straight into the ghost slots: zero unpack
+         NK(h->nccl->Recv(P.delv_xi + (size_t)a * P.allElem + f.ghost_off, f.count, ncclDouble, f.rank,
+                          h->comm, h->comm_stream));
+         NK(h->nccl->Send(h->mq_send + f.send_off + (size_t)a * f.count, f.count, ncclDouble, f.rank,
+                          h->comm, h->comm_stream));
+      }
+   NK(h->nccl->GroupEnd());
+   CK(cudaEventRecord(h->ev_b, h->comm_stream));
+   CK(cudaStreamWaitEvent(h->stream, h->ev_b, 0));
+   h->launches += 1;
+   return 0;
+}
+
+// enqueue one TimeIncrement + LagrangeLeapFrog on h->stream (no host sync)
+static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
+{
+   const KParams &P = h->P;
+   cudaStream_t s = h->stream;
+   const int dbg = h->debug;
+   if (marks) CK(cudaEventRecord(marks[0], s));
+   if (h->numRanks == 1) {
+      k_time_increment<<<1, 32, 0, s>>>(P.ctl, 0);
+   } else {
+      k_time_increment<<<1, 32, 0, s>>>(P.ctl, 1);
+      NK(h->nccl->AllReduce(&P.ctl->gnewdt, &P.ctl->gnewdt, 1, ncclDouble, ncclMin, h->comm, s));
+      k_time_increment<<<1, 32, 0, s>>>(P.ctl, 2);
+      h->launches += 2;
+   }
+   if (marks) CK(cudaEventRecord(marks[1], s));
+   k_force<<<blocks_for(P.ne, K1_THREADS), K1_THREADS, 0, s>>>(P);
+   if (marks) CK(cudaEventRecord(marks[2], s));
+   if (h->numRanks > 1) {
+      int rc;
+      k_node_boundary_gather<<<blocks_for(P.nbnode, 128), 128, 0, s>>>(P);
+      if ((rc = exchange_nodes(h))) return rc;
+      k_node<<<blocks_for(P.nn, K2_THREADS), K2_THREADS, 0, s>>>(P, dbg);   // interior, overlaps the exchange
+      CK(cudaStreamWaitEvent(s, h->ev_b, 0));
+      k_node_boundary_update<<<blocks_for(P.nbnode, 128), 128, 0, s>>>(P, dbg);
+      h->launches += 3;
+   } else {
+      k_node<<<blocks_for(P.nn, K2_THREADS), K2_THREADS, 0, s>>>(P, dbg);
+   }
+   if (marks) CK(cudaEventRecord(marks[3], s));
+   k_kinematics<<<blocks_for(P.ne, K3_THREADS), K3_THREADS, 0, s>>>(P);
+   if (h->numRanks > 1) {
+      int rc;
+      if ((rc = exchange_monoq(h))) return rc;
+      h->launches += 1;
+   }
+   if (marks) CK(cudaEventRecord(marks[4], s));
+   k_material<<<P.numWorkBlocks, MAT_THREADS, 0, s>>>(P, dbg);
+   if (marks) CK(cudaEventRecord(marks[5], s));
+   h->launches += 5;
+   CK(cudaGetLastError());
+   return 0;
+}
+
+static int ensure_graph(lulesh_b200 *h)
+{
+   if (h->graph && h->graph_debug == h->debug) return 0;
+   if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+   cudaGraph_t g;
+   const int64_t saved = h->launches;
+   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+   int rc = enqueue_cycle(h, nullptr);
+   cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+   h->launches = saved;
+   if (rc) return rc;
+   if (e != cudaSuccess) return fail(LULESH_B200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+   CK(cudaGraphInstantiate(&h->graph, g, 0));
+   CK(cudaGraphDestroy(g));
+   h->graph_debug = h->debug;
+   return 0;
+}
+
+static bool use_graph(const lulesh_b200 *h)
+{
+   static const bool disabled = getenv("LULESH_B200_NO_GRAPH") != nullptr;
+   return h->numRanks == 1 && !disabled;
+}
+
+static int enqueue_cycles(lulesh_b200 *h, int n)
+{
+   int rc;
+   if (use_graph(h)) {
+      if ((rc = ensure_graph(h))) return rc;
+      for (int i = 0; i < n; ++i) CK(cudaGraphLaunch(h->graph, h->stream));
+      h->launches += (int64_t)5 * n;
+   } else {
+      for (int i = 0; i < n; ++i)
+         if ((rc = enqueue_cycle(h, nullptr))) return rc;
+   }
+   return 0;
+}
+
+static int fetch_ctl(lulesh_b200 *h)
+{
+   CK(cudaMemcpyAsync(h->h_ctl, h->P.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+   CK(cudaStreamSynchronize(h->stream));
+   return 0;
+}
+
+static int set_max_cycles(lulesh_b200 *h, int max_cycles)
+{
+   CK(cudaMemcpyAsync(&h->P.ctl->max_cycles, &max_cycles, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+   return 0;
+}
+
+extern "C" int lulesh_b200_sum_nodal_mass(lulesh_b200 *h)
+{
+   if (!h) return fail(LULESH_B200_EINVAL, "null handle");
+   if (h->numRanks == 1) return 0;
+   CK(cudaSetDevice(h->device));
+   const KParams &P = h->P;
+   double *mass = h->field_ptr[LULESH_F_NODALMASS];
+   // own partial mass into the first plane of fhalo (the exchange ships 3 planes;
+   // the other two carry the same values and are ignored)
+   for (int a = 0; a < 3; ++a)
+      k_gather_index<<<blocks_for(P.nbnode, 256), 256, 0, h->stream>>>(
+         P.fhalo + (size_t)a * P.nbnode, mass, P.bnode, P.nbnode);
+   int rc;
+   if ((rc = exchange_nodes(h))) return rc;
+   CK(cudaStreamWaitEvent(h->stream, h->ev_b, 0));
+   k_boundary_mass<<<blocks_for(P.nbnode, 128), 128, 0, h->stream>>>(P, mass);
+   CK(cudaStreamSynchronize(h->stream));   // doubles as the MPI_Barrier of lulesh.cc:2732
+   return 0;
+}
+
+extern "C" int lulesh_b200_run(lulesh_b200 *h, int32_t max_cycles, int32_t sync_every,
+                               lulesh_b200_progress_cb cb, void *user)
+{
+   if (!h) return fail(LULESH_B200_EINVAL, "null handle");
+   CK(cudaSetDevice(h->device));
+   int rc;
+   if ((rc = set_max_cycles(h, max_cycles))) return rc;
+   if (sync_every <= 0) sync_every = 64;
+   if (cb) sync_every = 1;
+   if ((rc = fetch_ctl(h))) return rc;
+   while (h->h_ctl->error == 0 && h->h_ctl->time < h->h_ctl->stoptime && h->h_ctl->cycle < max_cycles) {
+      const int before = h->h_ctl->cycle;
+      const int batch = std::min<int>(sync_every, max_cycles - before);
+      if ((rc = enqueue_cycles(h, batch))) return rc;
+      if ((rc = fetch_ctl(h))) return rc;
+      if (cb && h->h_ctl->cycle != before) cb(h->h_ctl->cycle, h->h_ctl->time, h->h_ctl->deltatime, user);
+   }
+   return h->h_ctl->error;
+}
+
+extern "C" int lulesh_b200_step(lulesh_b200 *h)
+{
+   if (!h) return fail(LULESH_B200_EINVAL, "null handle");
+   CK(cudaSetDevice(h->device));
+   int rc;
+   if ((rc = set_max_cycles(h, INT_MAX))) return rc;
+   if ((rc = enqueue_cycles(h, 1))) return rc;
+   if ((rc = fetch_ctl(h))) return rc;
+   return h->h_ctl->error;
+}
+
+extern "C" int lulesh_b200_time_cycles(lulesh_b200 *h, int32_t cycles, float *total_ms,
+                                       float *per_kernel_ms, int64_t *launches)
+{
+   if (!h || cycles < 0) return fail(LULESH_B200_EINVAL, "bad argument");
+   CK(cudaSetDevice(h->device));
+   int rc;
+   if ((rc = set_max_cycles(h, INT_MAX))) return rc;
+   const int64_t l0 = h->launches;
+   if (!per_kernel_ms) {
+      if (use_graph(h) && (rc = ensure_graph(h))) return rc;
+      CK(cudaStreamSynchronize(h->stream));
+      CK(cudaEventRecord(h->ev_t0, h->stream));
+      if ((rc = enqueue_cycles(h, cycles))) return rc;
+      CK(cudaEventRecord(h->ev_t1, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      if (total_ms) CK(cudaEventElapsedTime(total_ms, h->ev_t0, h->ev_t1));
+   } else {
+      cudaEvent_t marks[6];
+      for (auto &m : marks) CK(cudaEventCreate(&m));
+      for (int k = 0; k < LULESH_B200_NUM_KERNELS; ++k) per_kernel_ms[k] = 0.f;
+      float total = 0.f;
+      for (int i = 0; i < cycles; ++i) {
+         if ((rc = enqueue_cycle(h, marks))) return rc;
+         CK(cudaStreamSynchronize(h->stream));
+         for (int k = 0; k < LULESH_B200_NUM_KERNELS; ++k) {
+            float ms;
+            CK(cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
+            per_kernel_ms[k] += ms;
+            total += ms;
+         }
+      }
+      for (auto &m : marks) cudaEventDestroy(m);
+      if (total_ms) *total_ms = total;
+   }
+   if (launches) *launches = h->launches - l0;
+   if ((rc = fetch_ctl(h))) return rc;
+   return h->h_ctl->error;
+}
+
+// --------------------------------------------------------------------------
+// scalars, fields, per-kernel entry points
+// --------------------------------------------------------------------------
+extern "C" int lulesh_b200_get_scalars(lulesh_b200 *h, lulesh_b200_scalars *out)
+{
+   if (!h || !out) return fail(LULESH_B200_EINVAL, "null argument");
+   CK(cudaSetDevice(h->device));
+   int rc;
+   if ((rc = fetch_ctl(h))) return rc;
+   const Ctl &c = *h->h_ctl;
+   memcpy(&out->dtcourant, &c.dtcourant_bits, 8);
+   memcpy(&out->dthydro, &c.dthydro_bits, 8);
+   out->dtfixed = c.dtfixed; out->time = c.time; out->deltatime = c.deltatime;
+   out->deltatimemultlb = c.deltatimemultlb; out->deltatimemultub = c.deltatimemultub;
+   out->dtmax = c.dtmax; out->stoptime = c.stoptime; out->cycle = c.cycle; out->error = c.error;
+   return 0;
+}
+
+extern "C" int lulesh_b200_set_scalars(lulesh_b200 *h, const lulesh_b200_scalars *in)
+{
+   if (!h || !in) return fail(LULESH_B200_EINVAL, "null argument");
+   CK(cudaSetDevice(h->device));
+   int rc;
+   if ((rc = fetch_ctl(h))) return rc;
+   Ctl c = *h->h_ctl;
+   memcpy(&c.dtcourant_bits, &in->dtcourant, 8);
+   memcpy(&c.dthydro_bits, &in->dthydro, 8);
+   c.dtfixed = in->dtfixed; c.time = in->time; c.deltatime = in->deltatime;
+   c.deltatimemultlb = in->deltatimemultlb; c.deltatimemultub = in->deltatimemultub;
+   c.dtmax = in->dtmax; c.stoptime = in->stoptime; c.cycle = in->cycle; c.error = in->error;
+   c.done = 0;
+   CK(cudaMemcpy(h->P.ctl, &c, sizeof c, cudaMemcpyHostToDevice));
+   return 0;
+}
+
+extern "C" size_t lulesh_b200_field_count(lulesh_b200 *h, int field)
+{
+   if (!h || field < 0 || field >= LULESH_F_COUNT) return 0;
+   return h->field_cnt[field];
+}
+
+extern "C" int lulesh_b200_download(lulesh_b200 *h, int field, double *dst, size_t count)
+{
+   if (!h || !dst || field < 0 || field >= LULESH_F_COUNT) return fail(LULESH_B200_EINVAL, "bad argument");
+   if (count != h->field_cnt[field])
+      return fail(LULESH_B200_EINVAL, "field %d has %zu entries, not %zu", field, h->field_cnt[field], count);
+   CK(cudaSetDevice(h->device));
+   CK(cudaStreamSynchronize(h->stream));
+   CK(cudaMemcpy(dst, h->field_ptr[field], count * sizeof(double), cudaMemcpyDeviceToHost));
+   return 0;
+}
+
+extern "C" int lulesh_b200_upload(lulesh_b200 *h, int field, const double *src, size_t count)
+{
+   if (!h || !src || field < 0 || field >= LULESH_F_COUNT) return fail(LULESH_B200_EINVAL, "bad argument");
+   if (count != h->field_cnt[field])
+      return fail(LULESH_B200_EINVAL, "field %d has %zu entries, not %zu", field, h->field_cnt[field], count);
+   CK(cudaSetDevice(h->device));
+   CK(cudaStreamSynchronize(h->stream));
+   CK(cudaMemcpy(h->field_ptr[field], src, count * sizeof(double), cudaMemcpyHostToDevice));
+   return 0;
+}
+
+extern "C" int lulesh_b200_set_debug(lulesh_b200 *h, int on)
+{
+   if (!h) return fail(LULESH_B200_EINVAL, "null handle");
+   h->debug = on ? 1 : 0;
+   return 0;
+}
+
+static int finish_kernel(lulesh_b200 *h)
+{
+   CK(cudaGetLastError());
+   int rc;
+   if ((rc = fetch_ctl(h))) return rc;
+   return h->h_ctl->error;
+}
+
+extern "C" int lulesh_b200_kernel_time_increment(lulesh_b200 *h)
+{
+   if (!h) return fail(LULESH_B200_EINVAL, "null handle");
+   if (h->numRanks != 1) return fail(LULESH_B200_EINVAL, "per-kernel entry points are single-rank");
+   CK(cudaSetDevice(h->device));
+   int rc;
+   if ((rc = set_max_cycles(h, INT_MAX))) return rc;
+   k_time_increment<<<1, 32, 0, h->stream>>>(h->P.ctl, 0);
+   return finish_kernel(h);
+}
+
+extern "C" int lulesh_b200_kernel_force(lulesh_b200 *h)
+{
+   if (!h) return fail(LULESH_B200_EINVAL, "null handle");
+   CK(cudaSetDevice(h->device));
+   k_force<<<blocks_for(h->P.ne, K1_THREADS), K1_THREADS, 0, h->stream>>>(h->P);
+   return finish_kernel(h);
+}
+
+extern "C" int lulesh_b200_kernel_node(lulesh_b200 *h, int materialise_debug)
+{
+   if (!h) return fail(LULESH_B200_EINVAL, "null handle");
+   if (h->numRanks != 1) return fail(LULESH_B200_EINVAL, "per-kernel entry points are single-rank");
+   CK(cudaSetDevice(h->device));
+   k_node<<<blocks_for(h->P.nn, K2_THREADS), K2_THREADS, 0, h->stream>>>(h->P, materialise_debug);
+   return finish_kernel(h);
+}
+
+extern "C" int lulesh_b200_kernel_kinematics(lulesh_b200 *h)
+{
+   if (!h) return fail(LULESH_B200_EINVAL, "null handle");
+   CK(cudaSetDevice(h->device));
+   k_kinematics<<<blocks_for(h->P.ne, K3_THREADS), K3_THREADS, 0, h->stream>>>(h->P);
+   return finish_kernel(h);
+}
+
+extern "C" int lulesh_b200_kernel_material(lulesh_b200 *h)
+{
+   if (!h) return fail(LULESH_B200_EINVAL, "null handle");
+   if (h->numRanks != 1) return fail(LULESH_B200_EINVAL, "per-kernel entry points are single-rank");
+   CK(cudaSetDevice(h->device));
+   k_material<<<h->P.numWorkBlocks, MAT_THREADS, 0, h->stream>>>(h->P, 1);
+   return finish_kernel(h);
+}
+
+extern "C" size_t lulesh_b200_device_bytes(lulesh_b200 *h) { return h ? h->device_bytes : 0; }
+extern "C" size_t lulesh_b200_upload_bytes(lulesh_b200 *h) { return h ? h->upload_bytes : 0; }

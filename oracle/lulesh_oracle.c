@@ -855,12 +855,14 @@ ora_domain *ora_new(int numRanks, int rank, int px, int py, int pz, int sx, int 
       for (int j = 0; j < sy; ++j)
          for (int i = 0; i < sx; ++i, ++e) {
             int bc = 0;
-            d->lxim[e] = (i > 0) ? e - 1 : e;
-            d->lxip[e] = (i < sx - 1) ? e + 1 : e;
-            d->letam[e] = (j > 0) ? e - sx : e;
-            d->letap[e] = (j < sy - 1) ? e + sx : e;
-            d->lzetam[e] = (k > 0) ? e - sx * sy : e;
-            d->lzetap[e] = (k < sz - 1) ? e + sx * sy : e;
+            /* lulesh-init.cc:541-564: index arithmetic that "wraps" at brick faces;
+             * those entries are masked by elemBC and never dereferenced */
+            d->lxim[e] = (e >= 1) ? e - 1 : e;
+            d->lxip[e] = (e < ne - 1) ? e + 1 : e;
+            d->letam[e] = (e >= sx) ? e - sx : e;
+            d->letap[e] = (e < ne - sx) ? e + sx : e;
+            d->lzetam[e] = (e >= sx * sy) ? e - sx * sy : e;
+            d->lzetap[e] = (e < ne - sx * sy) ? e + sx * sy : e;
             if (k == 0) {
                if (d->plane == 0) bc |= ZETA_M_SYMM;
                else { bc |= ZETA_M_COMM; d->lzetam[e] = ghost[0] + j * sx + i; }

@@ -1,0 +1,245 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against
+the CPU oracle on the same inputs, against the committed reference goldens, and --
+at full bench sizes -- through size-independent properties.
+
+Tolerances.  The device code uses FMA contraction, the factored hourglass form and
+a fused stress+hourglass corner force, so it is not bit-identical to the FMA-free
+reference; per-kernel outputs must agree to 1e-11 of the field's magnitude, run
+summaries to the north-star bar: identical cycle count, |e0 - e0_ref|/e0_ref <= 1e-8
+(we assert 1e-10), checksums within 1e-9 relative."""
+import json
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import load_npz
+
+pytestmark = pytest.mark.gpu
+
+KTOL = 1e-11
+
+
+def close(a, b, tol=KTOL, what=""):
+    scale = max(np.max(np.abs(b)), 1e-300)
+    err = np.max(np.abs(a - b)) / scale
+    assert err <= tol, f"{what}: max error {err:.3e} of field scale > {tol}"
+
+
+def seqsum(a):
+    return float(np.sum(a))
+
+
+@pytest.fixture(scope="module")
+def state9(lb):
+    """Device + oracle both loaded with the REFERENCE's state after 9 cycles of -s 8."""
+    c9 = load_npz("ref_s8_c9.npz")
+    dom = lb.Domain(8)
+    for name in "x y z xd yd zd e p q v ss".split():
+        dom.field(name)[:] = c9[name]
+    s = dom.scalars
+    s.time, s.deltatime, s.dtcourant, s.dthydro = c9["scalars"][:4]
+    s.cycle = 9
+    return dom, c9, load_npz("ref_s8_c10.npz")
+
+
+def test_kernels_one_by_one_against_reference_fixture(lb, state9):
+    dom, c9, c10 = state9
+    dev = lb.Device(dom)
+    dev.kernel("time_increment")
+    s = dev.scalars
+    assert s.cycle == 10
+    assert s.time == c10["scalars"][0] and s.deltatime == c10["scalars"][1]   # exact: same IEEE ops
+    dev.kernel("force")
+    dev.kernel("node", 1)
+    fscale = max(np.max(np.abs(c10[n])) for n in ("fx", "fy", "fz"))
+    for n in ("fx", "fy", "fz"):
+        assert np.max(np.abs(dev.download(n) - c10[n])) <= KTOL * fscale, n
+    ascale = max(np.max(np.abs(c10[n])) for n in ("xdd", "ydd", "zdd"))
+    for n in ("xdd", "ydd", "zdd"):
+        assert np.max(np.abs(dev.download(n) - c10[n])) <= KTOL * ascale, n
+    for n in "xd yd zd x y z".split():
+        close(dev.download(n), c10[n], what=n)
+    dev.kernel("kinematics")
+    for n in "vnew delv vdov arealg".split():
+        close(dev.download(n), c10[n], 1e-10, n)
+    dev.kernel("material")
+    for n in "ql qq e p q ss v".split():
+        close(dev.download(n), c10[n], 1e-10, n)
+    s = dev.scalars
+    assert abs(s.dtcourant - c10["scalars"][2]) <= 1e-11 * c10["scalars"][2]
+    assert abs(s.dthydro - c10["scalars"][3]) <= 1e-11 * c10["scalars"][3]
+    dev.close()
+
+
+def test_step_equals_kernel_sequence(lb, state9):
+    dom, _, c10 = state9
+    dev = lb.Device(dom)
+    dev.step()
+    for n in "x xd e p q ss v".split():
+        close(dev.download(n), c10[n], 1e-10, n)
+    assert dev.scalars.cycle == 10
+    dev.close()
+
+
+@pytest.mark.parametrize("nx,its,kw", [(7, 25, {}), (13, 30, dict(num_reg=16, balance=1, cost=8)),
+                                       (20, 15, dict(num_reg=1, cost=0)), (1, 5, {}), (2, 40, {})])
+def test_cycles_against_oracle(lb, oracle_mod, nx, its, kw):
+    """Seeded synthetic Sedov inputs, ragged sizes included (nx=1: a single element)."""
+    dom = lb.Domain(nx, **kw)
+    dev = lb.Device(dom)
+    dev.run(its)
+    ora = oracle_mod.OracleDomain(nx, kw.get("num_reg", 11), kw.get("balance", 1), kw.get("cost", 1))
+    assert ora.run(its) == 0
+    sd, so = dev.scalars, ora.scalars
+    assert sd.cycle == so.cycle
+    assert abs(sd.time - so.time) <= 1e-12 * so.time
+    assert abs(sd.deltatime - so.deltatime) <= 1e-9 * so.deltatime
+    for n in "x y z xd yd zd e p q v ss".split():
+        close(dev.download(n), ora.field(n), 1e-9, f"{n} (nx={nx})")
+    dev.close()
+
+
+@pytest.mark.parametrize("key,nx,its", [
+    ("lulesh_omp -s 30 -i 100", 30, 100), ("lulesh_omp -s 5", 5, 9999999),
+    ("lulesh_omp -s 10", 10, 9999999), ("lulesh_omp -s 20", 20, 9999999),
+    ("lulesh_omp -s 30 -r 1 -c 0", 30, 9999999), ("lulesh_omp -s 48 -i 20", 48, 20)])
+def test_runs_against_reference_goldens(lb, goldens, key, nx, its):
+    gold = goldens[key]
+    dom = lb.Domain(nx)
+    dev = lb.Device(dom)
+    dev.run(its)
+    s = dev.scalars
+    assert s.cycle == gold["cycles"]                                   # identical cycle count
+    e = dev.download("e")
+    assert abs(e[0] - gold["e0"]) / gold["e0"] <= 1e-10                 # bar: 1e-8
+    for name, key2 in (("e", "sum_e"), ("p", "sum_p"), ("q", "sum_q"), ("v", "sum_v"), ("ss", "sum_ss")):
+        got = seqsum(dev.download(name))
+        assert abs(got - gold[key2]) <= 1e-9 * abs(gold[key2]) + 1e-12, name
+    # symmetry figure (lulesh-util.cc:197-218): round-off level, same order as the reference's
+    plane = e[: nx * nx].reshape(nx, nx)
+    iu = np.triu_indices(nx, 1)
+    rel = np.abs(plane[iu] - plane.T[iu]) / plane.T[iu]
+    max_rel = float(np.nanmax(rel)) if rel.size else 0.0
+    assert max_rel <= max(10 * gold["max_rel_diff"], 1e-10)
+    dev.close()
+
+
+def test_long_goldens_if_present(lb, goldens):
+    """-s 90 run to stoptime (config-2 style check at a size the test budget allows)."""
+    key = "lulesh_omp -s 90 -r 1 -c 0"
+    if key not in goldens:
+        pytest.skip("golden not generated")
+    dev = lb.Device(lb.Domain(90))
+    dev.run()
+    assert dev.scalars.cycle == goldens[key]["cycles"]
+    assert abs(dev.download("e")[0] - goldens[key]["e0"]) / goldens[key]["e0"] <= 1e-8
+    dev.close()
+
+
+def test_region_flags_do_not_change_the_answer(lb):
+    """-r/-b/-c only change how much EOS work is done.  On the device the
+    per-element arithmetic is identical, so the results are bit-identical."""
+    out = []
+    for kw in (dict(num_reg=1, cost=0), dict(num_reg=16, balance=1, cost=8), dict(num_reg=21, balance=2, cost=3)):
+        dev = lb.Device(lb.Domain(24, **kw))
+        dev.run(60)
+        out.append((dev.download("e"), dev.download("p"), dev.download("x"), dev.scalars.time))
+        dev.close()
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and np.array_equal(o[1], out[0][1])
+        assert np.array_equal(o[2], out[0][2]) and o[3] == out[0][3]
+
+
+def test_run_is_deterministic_and_batching_invariant(lb):
+    res = []
+    for sync in (1, 7, 64):
+        dev = lb.Device(lb.Domain(16))
+        dev.run(50, sync_every=sync)
+        res.append((dev.download("e"), dev.download("xd"), dev.scalars.deltatime))
+        dev.close()
+    for r in res[1:]:
+        assert np.array_equal(r[0], res[0][0]) and np.array_equal(r[1], res[0][1]) and r[2] == res[0][2]
+
+
+def test_stoptime_termination_and_progress_callback(lb, goldens):
+    seen = []
+    dev = lb.Device(lb.Domain(5))
+    dev.run(progress=lambda c, t, dt: seen.append((c, t, dt)))
+    assert [c for c, _, _ in seen] == list(range(1, 73))      # -s 5 finishes in 72 cycles
+    assert seen[-1][1] == 1.0e-2 == dev.scalars.time          # lands exactly on stoptime
+    dev.run()                                                 # already finished: a no-op
+    assert dev.scalars.cycle == 72
+    dev.close()
+
+
+def test_error_codes_match_reference_exit_codes(lb):
+    dom = lb.Domain(6)
+    dom.field("v")[7] = -1.0
+    dev = lb.Device(dom)
+    with pytest.raises(lb.LuleshError) as e:
+        dev.step()
+    assert e.value.code == lb.VOLUME_ERROR
+    dev.close()
+    dom = lb.Domain(6)
+    dom.field("q")[11] = 2.0e12
+    dom.field("p")[11] = -2.0e12
+    dev = lb.Device(dom)
+    with pytest.raises(lb.LuleshError) as e:
+        dev.step()
+    assert e.value.code == lb.QSTOP_ERROR
+    dev.close()
+
+
+def test_upload_download_roundtrip_and_size_checks(lb):
+    dev = lb.Device(lb.Domain(4))
+    x = np.random.default_rng(0).random(dev.count("e"))
+    dev.upload("e", x)
+    assert np.array_equal(dev.download("e"), x)
+    with pytest.raises(lb.LuleshError):
+        dev.upload("e", x[:-1])
+    assert dev.count("delv_xi") == 64 + 6 * 16 and dev.count("x") == 125
+    dev.close()
+
+
+def test_full_size_properties_s128(lb):
+    """BASELINE config size (-s 128, 2.1M elements): properties the domain offers.
+    The Sedov problem is symmetric under any permutation of the axes; energy is
+    conserved to round-off by the staggered scheme up to the cut-offs; all volumes stay
+    positive; the run is reproducible bit for bit."""
+    nx, its = 128, 40
+    dev = lb.Device(lb.Domain(nx))
+    dev.run(its)
+    s = dev.scalars
+    assert s.cycle == its and s.error == 0
+    e = dev.download("e").reshape(nx, nx, nx)
+    scale = np.max(np.abs(e))
+    for perm in ((1, 0, 2), (2, 1, 0), (0, 2, 1)):
+        assert np.max(np.abs(e - e.transpose(perm))) <= 1e-9 * scale
+    v = dev.download("v")
+    assert np.all(v > 0)
+    volo = dev.download("volo")
+    assert abs(np.sum(v * volo) - 1.125 ** 3) <= 1e-9          # mesh still tiles the box (free faces barely move)
+    dev2 = lb.Device(lb.Domain(nx))
+    dev2.run(its)
+    assert np.array_equal(dev2.download("e").reshape(nx, nx, nx), e)
+    dev.close(); dev2.close()
+
+
+def test_driver_binary_report(lb, goldens):
+    p = subprocess.run([lb.BIN_PATH, "-s", "10"], capture_output=True, text=True,
+                       env={"LULESH_B200_FULL_PRECISION": "1", "PATH": "/usr/bin:/bin"})
+    assert p.returncode == 0, p.stderr
+    out = p.stdout
+    assert "Running problem size 10^3 per domain until completion" in out
+    assert "   Iteration count     =  231\n" in out
+    assert "   Final Origin Energy =  2.720531e+04\n" in out
+    assert "FOM                  = " in out and "(z/s)" in out
+    rec = json.loads([l for l in out.splitlines() if l.startswith("B200JSON ")][0][9:])
+    gold = goldens["lulesh_omp -s 10"]
+    assert rec["cycles"] == gold["cycles"] and abs(rec["e0"] - gold["e0"]) <= 1e-10 * gold["e0"]
+    q = subprocess.run([lb.BIN_PATH, "-s", "10", "-q"], capture_output=True, text=True)
+    assert q.returncode == 0 and q.stdout == ""
+    pr = subprocess.run([lb.BIN_PATH, "-s", "5", "-i", "3", "-p"], capture_output=True, text=True)
+    assert "cycle = 1, time = 3.417997e-04, dt=3.417997e-04" in pr.stdout
+    assert "cycle = 3, time = 8.925464e-04, dt=1.405871e-04" in pr.stdout

@@ -1,0 +1,133 @@
+"""Host side above the C ABI: the C++ Domain (lulesh_b200/csrc/host) against the
+reference's own setup (fixtures dumped from the reference Domain constructor) and
+against the oracle's independent setup; library loading and ABI surface; the
+driver's command-line behaviour (lulesh-util.cc:63-171)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_npz
+
+INT_FIELDS = "nodelist lxim lxip letam letap lzetam lzetap elemBC symmX symmY symmZ".split()
+
+
+def test_library_exports_every_declared_symbol(lb):
+    declared = set()
+    for hdr in ("lulesh_b200.h", "lulesh_host.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        declared |= set(re.findall(r"\b(lulesh_(?:b200|host)_[a-z_0-9]+)\s*\(", text))
+    declared -= {"lulesh_b200_progress_cb"}
+    assert declared == set(lb.ABI_SYMBOLS)
+    lib = ctypes.CDLL(lb.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_single_rank_setup_matches_reference_dump(lb):
+    ref = load_npz("ref_s8_c9.npz")   # connectivity and volo do not change with the cycle
+    d = lb.Domain(8)
+    for name in INT_FIELDS + ["regNumList"]:
+        assert np.array_equal(d.ints(name), ref[name]), name
+    for name in ("volo", "elemMass", "nodalMass"):
+        assert np.array_equal(d.field(name), ref[name]), name
+    assert list(d.ints("regElemSize")) == list(ref["regElemSize"])
+
+
+@pytest.mark.parametrize("rank", range(8))
+def test_multi_rank_setup_matches_reference_constructor(lb, rank):
+    """tp=2, nx=4: the reference Domain built for every rank location in a non-MPI
+    process (oracle/ref_setup_dump.cc).  Region lists are excluded: the non-MPI
+    reference does not rotate them by rank (lulesh-init.cc:408-409)."""
+    ref = load_npz(f"ref_setup_tp2_nx4_r{rank}.npz")
+    d = lb.Domain(4, num_ranks=8, rank=rank)
+    for name in INT_FIELDS:
+        got, want = d.ints(name), ref.get(name, np.zeros(0, np.int32))
+        assert np.array_equal(got, want), name
+    for name in ("x", "y", "z", "volo", "nodalMass", "e"):
+        assert np.array_equal(d.field(name), ref[name]), name
+    assert d.scalars.deltatime == ref["scalars"][1]   # dt0; identical on every rank here (F10)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(nx=6), dict(nx=5, num_reg=16, balance=1, cost=8), dict(nx=7, num_reg=1, cost=0),
+    dict(nx=4, num_ranks=2, rank=1), dict(nx=4, num_ranks=4, rank=2),
+    dict(nx=3, num_ranks=8, rank=5), dict(nx=4, num_ranks=2, rank=0, sizes=(6, 4, 3)),
+])
+def test_host_domain_equals_oracle_setup(lb, oracle_mod, kw):
+    d = lb.Domain(**kw)
+    nr = kw.get("num_ranks", 1)
+    o = oracle_mod.OracleDomain(kw["nx"], kw.get("num_reg", 11), kw.get("balance", 1),
+                                kw.get("cost", 1), num_ranks=nr, rank=kw.get("rank", 0),
+                                decomp=d.decomp, sizes=kw.get("sizes"))
+    for name in INT_FIELDS + ["regNumList", "regElemSize", "nodeElemStart", "nodeElemCornerList"]:
+        assert np.array_equal(d.ints(name), o.ints(name)), name
+    for name in "x y z xd yd zd nodalMass e p q v volo ss elemMass".split():
+        assert np.array_equal(d.field(name), o.field(name)), name
+    for r in range(kw.get("num_reg", 11)):
+        assert np.array_equal(d.region_list(r), o.region_list(r))
+    for n, _ in lb.Scalars._fields_:
+        assert getattr(d.scalars, n) == getattr(o.scalars, n), n
+
+
+def test_default_region_sizes_match_reference(lb, goldens):
+    d = lb.Domain(30)
+    assert list(d.ints("regElemSize")) == goldens["lulesh_omp -s 30 -i 100"]["regions"]
+    d = lb.Domain(12, 16, 1, 8)
+    assert list(d.ints("regElemSize")) == goldens["lulesh_omp -s 12 -i 40 -r 16 -b 1 -c 8"]["regions"]
+
+
+def test_corner_list_is_ascending_elements(lb):
+    d = lb.Domain(5)
+    start, corners = d.ints("nodeElemStart"), d.ints("nodeElemCornerList")
+    nodelist = d.ints("nodelist")
+    assert start[-1] == 8 * d.numElem
+    for n in range(d.numNode):
+        seg = corners[start[n]:start[n + 1]]
+        assert 1 <= len(seg) <= 8 and np.all(np.diff(seg // 8) > 0)
+        assert np.all(nodelist[seg] == n)
+
+
+def test_decompose(lb):
+    assert lb.decompose(1) == (1, 1, 1) and lb.decompose(8) == (2, 2, 2)
+    assert lb.decompose(2) == (1, 1, 2) and lb.decompose(4) == (1, 2, 2)
+    assert lb.decompose(27) == (3, 3, 3)
+    with pytest.raises(ValueError):
+        lb.decompose(3)
+
+
+def test_invalid_domain_arguments(lb):
+    with pytest.raises(ValueError):
+        lb.Domain(0)
+    with pytest.raises(ValueError):
+        lb.Domain(4, num_ranks=2, rank=2)
+
+
+def test_create_fails_loudly_without_gpu(lb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(lb.LuleshError) as e:
+        lb.Device(lb.Domain(4))
+    assert e.value.code == lb.ECUDA and "no CPU fallback" in str(e.value)
+
+
+def _cli(lb, *args):
+    return subprocess.run([lb.BIN_PATH, *args], capture_output=True, text=True)
+
+
+def test_cli_help_and_errors(lb):
+    p = _cli(lb, "-h")
+    assert p.returncode == 0 and p.stdout.startswith("Usage: ") and " -q              : quiet mode" in p.stdout
+    p = _cli(lb, "-z")
+    assert p.returncode == 255 and "ERROR: Unknown command line argument: -z" in p.stdout
+    p = _cli(lb, "-s")
+    assert p.returncode == 255 and "Missing integer argument to -s" in p.stdout
+    p = _cli(lb, "-i", "2x")
+    assert p.returncode == 255
+    assert "Parse Error on option -i integer value required after argument" in p.stdout
+    p = _cli(lb, "-v")
+    assert p.returncode == 255 and "Use of -v requires compiling with -DVIZ_MESH" in p.stdout
