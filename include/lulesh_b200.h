@@ -213,6 +213,23 @@ int lulesh_b200_time_cycles(lulesh_b200 *h, int32_t cycles, float *total_ms,
 size_t lulesh_b200_device_bytes(lulesh_b200 *h);
 size_t lulesh_b200_upload_bytes(lulesh_b200 *h);
 
+/* Host-only description of the multi-rank exchanges of one rank (no GPU, no NCCL
+ * needed): who shares which nodes / face layers and in which canonical order
+ * the partial sums are added.  Replaces the index arithmetic of
+ * lulesh-comm.cc:59-1835; exposed so it can be tested on CPU.  Arrays (int32):
+ *   bnode[nb]            node ids shared with at least one other rank
+ *   pack_idx[send_total] send slot -> index into the rank's own [3][nb] partials
+ *   msg_rank/count/send_off/recv_off  one entry per neighbour (26 max)
+ *   bsum_start[nb+1], bsum_src[2*k]   CSR of (base, stride) pairs into the halo
+ *                        buffer [own 3*nb | received messages], ascending source rank
+ *   mq_idx[mq_total]     MonoQ send slot -> index into delv_xi|eta|zeta ([3][allElem])
+ *   face_rank/count/send_off/ghost_off  one entry per face neighbour (6 max) */
+typedef struct lulesh_b200_halo_plan lulesh_b200_halo_plan;
+int lulesh_b200_halo_plan_create(const lulesh_b200_host_view *view, lulesh_b200_halo_plan **out);
+int lulesh_b200_halo_plan_query(const lulesh_b200_halo_plan *plan, const char *what,
+                                const int32_t **data, size_t *count);
+void lulesh_b200_halo_plan_destroy(lulesh_b200_halo_plan *plan);
+
 const char *lulesh_b200_last_error(void);
 
 /* Replaces ~Domain (lulesh-init.cc:198-213) for the device side. */

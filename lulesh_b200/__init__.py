@@ -85,6 +85,7 @@ ABI_SYMBOLS = (
     "lulesh_b200_kernel_time_increment lulesh_b200_kernel_force lulesh_b200_kernel_node "
     "lulesh_b200_kernel_kinematics lulesh_b200_kernel_material lulesh_b200_time_cycles "
     "lulesh_b200_device_bytes lulesh_b200_upload_bytes lulesh_b200_last_error "
+    "lulesh_b200_halo_plan_create lulesh_b200_halo_plan_query lulesh_b200_halo_plan_destroy "
     "lulesh_b200_destroy "
     "lulesh_host_domain_new lulesh_host_domain_free lulesh_host_domain_view "
     "lulesh_host_domain_field lulesh_host_domain_ints lulesh_host_domain_scalars "
@@ -119,6 +120,9 @@ _sig("lulesh_b200_device_bytes", C.c_size_t, _vp)
 _sig("lulesh_b200_upload_bytes", C.c_size_t, _vp)
 _sig("lulesh_b200_last_error", C.c_char_p)
 _sig("lulesh_b200_destroy", None, _vp)
+_sig("lulesh_b200_halo_plan_create", C.c_int, C.POINTER(HostView), C.POINTER(_vp))
+_sig("lulesh_b200_halo_plan_query", C.c_int, _vp, C.c_char_p, C.POINTER(_pi), C.POINTER(C.c_size_t))
+_sig("lulesh_b200_halo_plan_destroy", None, _vp)
 _sig("lulesh_host_domain_new", _vp, *([C.c_int] * 11))
 _sig("lulesh_host_domain_free", None, _vp)
 _sig("lulesh_host_domain_view", None, _vp, C.POINTER(HostView))
@@ -202,6 +206,28 @@ class Domain:
         if getattr(self, "_p", None):
             _lib.lulesh_host_domain_free(self._p)
             self._p = None
+
+
+HALO_ARRAYS = ("bnode bsum_start bsum_src pack_idx msg_rank msg_count msg_send_off msg_recv_off "
+               "mq_idx face_rank face_count face_send_off face_ghost_off").split()
+
+
+def halo_plan(domain: Domain) -> dict:
+    """Host-only halo description of one rank (lulesh_b200_halo_plan_*), as numpy arrays."""
+    p = _vp()
+    rc = _lib.lulesh_b200_halo_plan_create(C.byref(domain.refresh_view()), C.byref(p))
+    if rc:
+        raise LuleshError(rc, "halo_plan_create")
+    out = {}
+    for name in HALO_ARRAYS:
+        data, n = _pi(), C.c_size_t()
+        rc = _lib.lulesh_b200_halo_plan_query(p, name.encode(), C.byref(data), C.byref(n))
+        if rc:
+            raise LuleshError(rc, "halo_plan_query")
+        out[name] = (np.ctypeslib.as_array(data, shape=(n.value,)).copy() if n.value
+                     else np.zeros(0, np.int32))
+    _lib.lulesh_b200_halo_plan_destroy(p)
+    return out
 
 
 class Device:

@@ -426,6 +426,128 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    return 0;
 }
 
+// --------------------------------------------------------------------------
+// Halo plan: everything the multi-rank path needs to know about who shares what,
+// computed on the host from the view alone (no GPU, no NCCL) so that it can be
+// unit-tested on CPU (tests/test_multirank_cpu.py drives it over gloo).
+//
+// Node exchange (replaces CommSend/CommSBN, lulesh-comm.cc:357-1257): for every
+// existing neighbour one message of 3 planes x count values; receivers sum ALL
+// ranks' partials of a shared node in ascending-rank order, so the result is
+// bit-identical on every sharing rank and the reference's CommSyncPosVel
+// (lulesh-comm.cc:1261-1680) is unnecessary.
+// MonoQ exchange (CommMonoQ, lulesh-comm.cc:1684-1835): face neighbours only,
+// received straight into the ghost slots of delv_xi/eta/zeta.
+// --------------------------------------------------------------------------
+struct lulesh_b200_halo_plan {
+   std::vector<int> bnode, bsum_start, bsum_src, pack_idx;
+   std::vector<int> msg_rank, msg_count, msg_send_off, msg_recv_off;
+   std::vector<int> mq_idx, face_rank, face_count, face_send_off, face_ghost_off;
+   int fhalo_size = 0, send_total = 0, mq_total = 0;
+};
+
+static int build_halo_plan(const lulesh_b200_host_view *v, lulesh_b200_halo_plan &pl)
+{
+   const int nn = v->numNode;
+   const int allElem = v->numElem + 2 * v->sizeX * v->sizeY + 2 * v->sizeX * v->sizeZ +
+                       2 * v->sizeY * v->sizeZ;
+   std::vector<int> bmap(nn, -1);
+   struct Dir { int rank; std::vector<int> nodes; };
+   std::vector<Dir> dirs;
+   for (int q = 0; q < 26; ++q) {
+      const int nb = neighbour_rank(v, k_dirs[q]);
+      if (nb < 0) continue;
+      Dir d{nb, {}};
+      shared_nodes(v, k_dirs[q], d.nodes);
+      for (int n : d.nodes) bmap[n] = 0;
+      dirs.push_back(std::move(d));
+   }
+   for (int n = 0; n < nn; ++n)
+      if (bmap[n] == 0) { bmap[n] = (int)pl.bnode.size(); pl.bnode.push_back(n); }
+   const int nb = (int)pl.bnode.size();
+
+   long long send_off = 0, recv_off = (long long)3 * nb;
+   struct Contribution { int rank, base, stride; };
+   std::vector<std::vector<Contribution>> contrib(nb);
+   for (int b = 0; b < nb; ++b) contrib[b].push_back({v->rank, b, nb});
+   for (const Dir &d : dirs) {
+      const int cnt = (int)d.nodes.size();
+      if (recv_off + 3LL * cnt > INT_MAX) return fail(LULESH_B200_EINVAL, "halo too large");
+      pl.msg_rank.push_back(d.rank); pl.msg_count.push_back(cnt);
+      pl.msg_send_off.push_back((int)send_off); pl.msg_recv_off.push_back((int)recv_off);
+      for (int a = 0; a < 3; ++a)
+         for (int t = 0; t < cnt; ++t) pl.pack_idx.push_back(a * nb + bmap[d.nodes[t]]);
+      for (int t = 0; t < cnt; ++t) contrib[bmap[d.nodes[t]]].push_back({d.rank, (int)(recv_off + t), cnt});
+      send_off += 3LL * cnt;
+      recv_off += 3LL * cnt;
+   }
+   pl.send_total = (int)send_off;
+   pl.fhalo_size = (int)recv_off;
+   pl.bsum_start.assign(nb + 1, 0);
+   for (int b = 0; b < nb; ++b) {
+      std::stable_sort(contrib[b].begin(), contrib[b].end(),
+                       [](const Contribution &x, const Contribution &y) { return x.rank < y.rank; });
+      for (const Contribution &c : contrib[b]) { pl.bsum_src.push_back(c.base); pl.bsum_src.push_back(c.stride); }
+      pl.bsum_start[b + 1] = (int)(pl.bsum_src.size() / 2);
+   }
+
+   long long mq_off = 0, ghost = v->numElem;
+   std::vector<int> elems;
+   for (int q = 0; q < 6; ++q) {   // ghost blocks in pMin,pMax,rMin,rMax,cMin,cMax order
+      const int nbr = neighbour_rank(v, k_dirs[q]);
+      if (nbr < 0) continue;
+      face_elems(v, k_dirs[q], elems);
+      const int cnt = (int)elems.size();
+      pl.face_rank.push_back(nbr); pl.face_count.push_back(cnt);
+      pl.face_send_off.push_back((int)mq_off); pl.face_ghost_off.push_back((int)ghost);
+      for (int a = 0; a < 3; ++a)
+         for (int e : elems) pl.mq_idx.push_back(a * allElem + e);
+      mq_off += 3LL * cnt;
+      ghost += cnt;
+   }
+   pl.mq_total = (int)mq_off;
+   return 0;
+}
+
+static bool view_is_sane(const lulesh_b200_host_view *v)
+{
+   return v && v->abi_version == LULESH_B200_ABI_VERSION && v->numElem > 0 && v->numNode > 0 &&
+          (long long)v->sizeX * v->sizeY * v->sizeZ == v->numElem &&
+          (long long)(v->sizeX + 1) * (v->sizeY + 1) * (v->sizeZ + 1) == v->numNode &&
+          v->numRanks >= 1 && v->px * v->py * v->pz == v->numRanks && v->rank >= 0 &&
+          v->rank < v->numRanks &&
+          v->rank == v->planeLoc * v->px * v->py + v->rowLoc * v->px + v->colLoc;
+}
+
+extern "C" int lulesh_b200_halo_plan_create(const lulesh_b200_host_view *view,
+                                            lulesh_b200_halo_plan **out)
+{
+   if (!out || !view_is_sane(view)) return fail(LULESH_B200_EINVAL, "bad view for halo plan");
+   lulesh_b200_halo_plan *pl = new lulesh_b200_halo_plan();
+   const int rc = build_halo_plan(view, *pl);
+   if (rc) { delete pl; return rc; }
+   *out = pl;
+   return 0;
+}
+
+extern "C" int lulesh_b200_halo_plan_query(const lulesh_b200_halo_plan *pl, const char *what,
+                                           const int32_t **data, size_t *count)
+{
+   if (!pl || !what || !data || !count) return fail(LULESH_B200_EINVAL, "null argument");
+   struct Entry { const char *name; const std::vector<int> *v; };
+   const Entry table[] = {
+      {"bnode", &pl->bnode}, {"bsum_start", &pl->bsum_start}, {"bsum_src", &pl->bsum_src},
+      {"pack_idx", &pl->pack_idx}, {"msg_rank", &pl->msg_rank}, {"msg_count", &pl->msg_count},
+      {"msg_send_off", &pl->msg_send_off}, {"msg_recv_off", &pl->msg_recv_off},
+      {"mq_idx", &pl->mq_idx}, {"face_rank", &pl->face_rank}, {"face_count", &pl->face_count},
+      {"face_send_off", &pl->face_send_off}, {"face_ghost_off", &pl->face_ghost_off}};
+   for (const Entry &e : table)
+      if (!strcmp(e.name, what)) { *data = e.v->data(); *count = e.v->size(); return 0; }
+   return fail(LULESH_B200_EINVAL, "unknown halo plan array '%s'", what);
+}
+
+extern "C" void lulesh_b200_halo_plan_destroy(lulesh_b200_halo_plan *pl) { delete pl; }
+
 static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void *unique_id,
                       std::vector<unsigned char> &nodeFlags)
 {
@@ -435,78 +557,29 @@ static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void
    h->nccl = nccl_api();
    if (!h->nccl) return fail(LULESH_B200_ENCCL, "libnccl.so.2 could not be loaded");
 
-   // ---- node halo: boundary-node numbering, messages, canonical contribution lists
-   const int nn = v->numNode;
-   std::vector<int> bmap(nn, -1), nodes;
-   struct Dir { int q, rank; std::vector<int> nodes; };
-   std::vector<Dir> dirs;
-   for (int q = 0; q < 26; ++q) {
-      const int nb = neighbour_rank(v, k_dirs[q]);
-      if (nb < 0) continue;
-      Dir d{q, nb, {}};
-      shared_nodes(v, k_dirs[q], d.nodes);
-      for (int n : d.nodes) bmap[n] = 0;
-      dirs.push_back(std::move(d));
-   }
-   std::vector<int> bnode;
-   for (int n = 0; n < nn; ++n)
-      if (bmap[n] == 0) { bmap[n] = (int)bnode.size(); bnode.push_back(n); nodeFlags[n] |= NODE_COMM; }
-   const int nb = (int)bnode.size();
-   P.nbnode = nb;
-
-   size_t send_off = 0, recv_off = (size_t)3 * nb;
-   std::vector<int> pack_idx;
-   struct Contribution { int rank, base, stride; };
-   std::vector<std::vector<Contribution>> contrib(nb);
-   for (int b = 0; b < nb; ++b) contrib[b].push_back({v->rank, b, nb});
-   for (const Dir &d : dirs) {
-      Message m{d.rank, (int)d.nodes.size(), send_off, recv_off};
-      for (int a = 0; a < 3; ++a)
-         for (int t = 0; t < m.count; ++t) pack_idx.push_back(a * nb + bmap[d.nodes[t]]);
-      for (int t = 0; t < m.count; ++t)
-         contrib[bmap[d.nodes[t]]].push_back({d.rank, (int)(recv_off + t), m.count});
-      send_off += (size_t)3 * m.count;
-      recv_off += (size_t)3 * m.count;
-      h->msgs.push_back(m);
-   }
-   if (recv_off > (size_t)INT_MAX) return fail(LULESH_B200_EINVAL, "halo too large");
-   h->send_total = send_off;
-   P.fhalo_stride = (int)recv_off;
-   std::vector<int> bsum_start(nb + 1, 0), bsum_src;
-   for (int b = 0; b < nb; ++b) {
-      std::stable_sort(contrib[b].begin(), contrib[b].end(),
-                       [](const Contribution &x, const Contribution &y) { return x.rank < y.rank; });
-      for (const Contribution &c : contrib[b]) { bsum_src.push_back(c.base); bsum_src.push_back(c.stride); }
-      bsum_start[b + 1] = (int)(bsum_src.size() / 2);
-   }
+   lulesh_b200_halo_plan pl;
+   if ((rc = build_halo_plan(v, pl))) return rc;
+   for (int n : pl.bnode) nodeFlags[n] |= NODE_COMM;
+   P.nbnode = (int)pl.bnode.size();
+   P.fhalo_stride = pl.fhalo_size;
+   h->send_total = pl.send_total;
+   h->mq_total = pl.mq_total;
+   for (size_t i = 0; i < pl.msg_rank.size(); ++i)
+      h->msgs.push_back({pl.msg_rank[i], pl.msg_count[i], (size_t)pl.msg_send_off[i], (size_t)pl.msg_recv_off[i]});
+   for (size_t i = 0; i < pl.face_rank.size(); ++i)
+      h->faces.push_back({pl.face_rank[i], pl.face_count[i], (size_t)pl.face_send_off[i], (size_t)pl.face_ghost_off[i]});
    int *pi;
-   if ((rc = dev_upload(h, &pi, bnode.data(), bnode.size()))) return rc;
+   if ((rc = dev_upload(h, &pi, pl.bnode.data(), pl.bnode.size()))) return rc;
    P.bnode = pi;
-   if ((rc = dev_upload(h, &pi, bsum_start.data(), bsum_start.size()))) return rc;
+   if ((rc = dev_upload(h, &pi, pl.bsum_start.data(), pl.bsum_start.size()))) return rc;
    P.bsum_start = pi;
-   if ((rc = dev_upload(h, &pi, bsum_src.data(), bsum_src.size()))) return rc;
+   if ((rc = dev_upload(h, &pi, pl.bsum_src.data(), pl.bsum_src.size()))) return rc;
    P.bsum_src = pi;
-   if ((rc = dev_upload(h, &h->pack_idx, pack_idx.data(), pack_idx.size()))) return rc;
-   if ((rc = dev_zero(h, &P.fhalo, recv_off))) return rc;
-   if ((rc = dev_zero(h, &h->sendbuf, send_off))) return rc;
-
-   // ---- MonoQ: face neighbours only; ghost blocks in pMin,pMax,rMin,rMax,cMin,cMax order
-   size_t mq_off = 0, ghost = (size_t)v->numElem;
-   std::vector<int> mq_idx, elems;
-   for (int q = 0; q < 6; ++q) {
-      const int nbr = neighbour_rank(v, k_dirs[q]);
-      if (nbr < 0) continue;
-      face_elems(v, k_dirs[q], elems);
-      FaceMessage f{nbr, (int)elems.size(), mq_off, ghost};
-      for (int a = 0; a < 3; ++a)
-         for (int e : elems) mq_idx.push_back(a * P.allElem + e);
-      mq_off += (size_t)3 * f.count;
-      ghost += f.count;
-      h->faces.push_back(f);
-   }
-   h->mq_total = mq_off;
-   if ((rc = dev_upload(h, &h->mq_idx, mq_idx.data(), mq_idx.size()))) return rc;
-   if ((rc = dev_zero(h, &h->mq_send, mq_off))) return rc;
+   if ((rc = dev_upload(h, &h->pack_idx, pl.pack_idx.data(), pl.pack_idx.size()))) return rc;
+   if ((rc = dev_zero(h, &P.fhalo, (size_t)pl.fhalo_size))) return rc;
+   if ((rc = dev_zero(h, &h->sendbuf, (size_t)pl.send_total))) return rc;
+   if ((rc = dev_upload(h, &h->mq_idx, pl.mq_idx.data(), pl.mq_idx.size()))) return rc;
+   if ((rc = dev_zero(h, &h->mq_send, (size_t)pl.mq_total))) return rc;
 
    ncclUniqueId id;
    memcpy(&id, unique_id, sizeof id);
