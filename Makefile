@@ -4,7 +4,8 @@
 NVCC    ?= /usr/local/cuda/bin/nvcc
 HOSTCXX := $(shell command -v /usr/bin/g++ || echo g++)
 ARCH    := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin $(HOSTCXX)
+KDEFS   ?=
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin $(HOSTCXX) $(KDEFS)
 CXXFLAGS := -O2 -std=c++17 -fPIC -ffp-contract=off -Wall
 CSRC := lulesh_b200/csrc
 OBJ  := build

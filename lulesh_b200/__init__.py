@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblulesh_b200.so")
+LIB_PATH = os.environ.get("LULESH_B200_LIB") or os.path.join(_HERE, "lib", "liblulesh_b200.so")
 BIN_PATH = os.path.join(_HERE, "bin", "lulesh_b200")
 
 if not os.path.exists(LIB_PATH):

@@ -140,6 +140,7 @@ struct lulesh_b200 {
    int *mq_idx = nullptr;
    size_t mq_total = 0;
    int64_t launches = 0;
+   int k1_grid = 0, k3_grid = 0;   // persistent grids: SMs x resident blocks (capped by the work)
 };
 
 template <typename T>
@@ -174,6 +175,8 @@ static int dev_zero(lulesh_b200 *h, T **out, size_t count)
    CK(cudaMemset(*out, 0, std::max<size_t>(count, 1) * sizeof(T)));
    return 0;
 }
+
+static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
 static int region_rep(int r, int numReg, int cost)   // lulesh.cc:2393-2400
 {
@@ -290,6 +293,7 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    P.ne_pad = (ne + 15) & ~15;
    P.nn_pad = (nn + 31) & ~31;
    P.c = v->constants;
+   P.unit_rho0 = (v->constants.refdens == 1.0) ? 1 : 0;
    int rc;
 
    // ---- control block
@@ -421,6 +425,18 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
       unsigned char *p_;
       if ((rc = dev_upload(h, &p_, nodeFlags.data(), nodeFlags.size()))) return rc;
       P.nodeFlags = p_;
+   }
+   {  // persistent grids for the cp.async-pipelined element kernels
+      int occ1 = 0, occ3 = 0;
+      CK(cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
+      CK(cudaFuncSetAttribute(k_kinematics, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES));
+      CK(cudaFuncSetAttribute(k_force, cudaFuncAttributePreferredSharedMemoryCarveout, 75));
+      CK(cudaFuncSetAttribute(k_kinematics, cudaFuncAttributePreferredSharedMemoryCarveout, 75));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_force, K1_THREADS, K1_SMEM_BYTES));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_kinematics, K3_THREADS, K3_SMEM_BYTES));
+      if (occ1 < 1 || occ3 < 1) return fail(LULESH_B200_ECUDA, "element kernels do not fit on an SM");
+      h->k1_grid = std::min(blocks_for(ne, K1_THREADS), prop.multiProcessorCount * occ1);
+      h->k3_grid = std::min(blocks_for(ne, K3_THREADS), prop.multiProcessorCount * occ3);
    }
    CK(cudaDeviceSynchronize());
    return 0;
@@ -620,7 +636,6 @@ extern "C" void lulesh_b200_destroy(lulesh_b200 *h)
 // --------------------------------------------------------------------------
 // the cycle
 // --------------------------------------------------------------------------
-static inline int blocks_for(int n, int t) { return (n + t - 1) / t; }
 
 // node-halo exchange of the three force planes (or the replicated mass)
 static int exchange_nodes(lulesh_b200 *h)
@@ -679,7 +694,7 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
       h->launches += 2;
    }
    if (marks) CK(cudaEventRecord(marks[1], s));
-   k_force<<<blocks_for(P.ne, K1_THREADS), K1_THREADS, 0, s>>>(P);
+   k_force<<<h->k1_grid, K1_THREADS, K1_SMEM_BYTES, s>>>(P);
    if (marks) CK(cudaEventRecord(marks[2], s));
    if (h->numRanks > 1) {
       int rc;
@@ -693,7 +708,7 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
       k_node<<<blocks_for(P.nn, K2_THREADS), K2_THREADS, 0, s>>>(P, dbg);
    }
    if (marks) CK(cudaEventRecord(marks[3], s));
-   k_kinematics<<<blocks_for(P.ne, K3_THREADS), K3_THREADS, 0, s>>>(P);
+   k_kinematics<<<h->k3_grid, K3_THREADS, K3_SMEM_BYTES, s>>>(P);
    if (h->numRanks > 1) {
       int rc;
       if ((rc = exchange_monoq(h))) return rc;
@@ -941,7 +956,7 @@ extern "C" int lulesh_b200_kernel_force(lulesh_b200 *h)
 {
    if (!h) return fail(LULESH_B200_EINVAL, "null handle");
    CK(cudaSetDevice(h->device));
-   k_force<<<blocks_for(h->P.ne, K1_THREADS), K1_THREADS, 0, h->stream>>>(h->P);
+   k_force<<<h->k1_grid, K1_THREADS, K1_SMEM_BYTES, h->stream>>>(h->P);
    return finish_kernel(h);
 }
 
@@ -958,7 +973,7 @@ extern "C" int lulesh_b200_kernel_kinematics(lulesh_b200 *h)
 {
    if (!h) return fail(LULESH_B200_EINVAL, "null handle");
    CK(cudaSetDevice(h->device));
-   k_kinematics<<<blocks_for(h->P.ne, K3_THREADS), K3_THREADS, 0, h->stream>>>(h->P);
+   k_kinematics<<<h->k3_grid, K3_THREADS, K3_SMEM_BYTES, h->stream>>>(h->P);
    return finish_kernel(h);
 }
 

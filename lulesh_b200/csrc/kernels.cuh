@@ -73,12 +73,29 @@ struct KParams {
    const int *bsum_src;           // index into fhalo planes (own slot or recv slot)
    double *fhalo;                 // [3][fhalo_stride]: own partials [0,nbnode) then recv slots
    int fhalo_stride;
+   int unit_rho0;                 // refdens == 1.0: EOS skips the exact no-op division
    lulesh_b200_constants c;
 };
 
-constexpr int K1_THREADS = 128;
+#ifndef LB_K1_THREADS
+#define LB_K1_THREADS 128
+#endif
+#ifndef LB_K3_THREADS
+#define LB_K3_THREADS 128
+#endif
+constexpr int K1_THREADS = LB_K1_THREADS;
+#ifndef LB_K1_BPS
+#define LB_K1_BPS 2
+#endif
+#ifndef LB_K3_BPS
+#define LB_K3_BPS 3
+#endif
+constexpr int K1_BLOCKS_PER_SM = LB_K1_BPS;
 constexpr int K2_THREADS = 256;
-constexpr int K3_THREADS = 128;
+constexpr int K3_THREADS = LB_K3_THREADS;
+constexpr int K3_BLOCKS_PER_SM = LB_K3_BPS;
+constexpr int K1_SMEM_BYTES = 54 * K1_THREADS * 8;   // cp.async staging tile: 48 node values + 6 scalars
+constexpr int K3_SMEM_BYTES = 50 * K3_THREADS * 8;   // 48 node values + volo, v
 constexpr int MAT_THREADS = 128;
 
 __global__ void k_time_increment(Ctl *ctl, int phase);
