@@ -1,0 +1,106 @@
+"""Multi-GPU parity (-m gpu, needs >= 2 devices; skipped otherwise): NCCL halo
+exchange path against the single-GPU run of the same GLOBAL mesh (the oracle for 2-
+and 4-rank layouts) and against the reference goldens via the
+8 x s/2 == s chain; shared nodes must be bit-identical on all ranks."""
+import json
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_ranks(lb, decomp, sizes, its, num_reg=11, balance=1, cost=1):
+    n = decomp[0] * decomp[1] * decomp[2]
+    uid = lb.get_unique_id()
+    out, errs = [None] * n, []
+
+    def body(r):
+        try:
+            dom = lb.Domain(sizes[0], num_reg, balance, cost, num_ranks=n, rank=r, decomp=decomp, sizes=sizes)
+            dev = lb.Device(dom, device=r, unique_id=uid)
+            dev.sum_nodal_mass()
+            dev.run(its)
+            out[r] = dict(s=dev.scalars, dom=dom,
+                          **{f: dev.download(f) for f in "x y z xd yd zd e p q v nodalMass".split()})
+            dev.close()
+        except Exception as ex:   # pragma: no cover
+            errs.append(ex)
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    return out
+
+
+def assemble(out, decomp, sizes, name):
+    """global element field from the per-rank bricks"""
+    px, py, pz = decomp
+    sx, sy, sz = sizes
+    g = np.zeros((pz * sz, py * sy, px * sx))
+    for r, o in enumerate(out):
+        c, w, p = r % px, (r // px) % py, r // (px * py)
+        g[p * sz:(p + 1) * sz, w * sy:(w + 1) * sy, c * sx:(c + 1) * sx] = o[name].reshape(sz, sy, sx)
+    return g
+
+
+@pytest.mark.parametrize("decomp,sizes,need", [((1, 1, 2), (24, 24, 12), 2), ((1, 2, 2), (24, 12, 12), 4),
+                                               ((2, 2, 2), (12, 12, 12), 8)])
+def test_ranks_match_single_gpu_global_run(lb, decomp, sizes, need):
+    if ngpu() < need:
+        pytest.skip(f"needs {need} GPUs")
+    its = 120
+    out = run_ranks(lb, decomp, sizes, its)
+    single = lb.Device(lb.Domain(24))
+    single.run(its)
+    s1 = single.scalars
+    for o in out:
+        assert o["s"].cycle == s1.cycle == its
+        assert o["s"].time == out[0]["s"].time and o["s"].deltatime == out[0]["s"].deltatime
+    assert abs(out[0]["s"].time - s1.time) <= 1e-13 * s1.time
+    for name in "e p q v".split():
+        g = assemble(out, decomp, sizes, name)
+        ref = single.download(name).reshape(24, 24, 24)
+        assert np.max(np.abs(g - ref)) <= 1e-9 * max(np.max(np.abs(ref)), 1e-300), name
+    single.close()
+    # shared nodes: bit-identical on both sides of every cut (replaces CommSyncPosVel)
+    plans = [lb.halo_plan(o["dom"]) for o in out]
+    for r, p in enumerate(plans):
+        for peer, cnt, soff in zip(p["msg_rank"], p["msg_count"], p["msg_send_off"]):
+            q = plans[peer]
+            j = list(q["msg_rank"]).index(r)
+            mine = p["bnode"][p["pack_idx"][soff:soff + cnt]]
+            theirs = q["bnode"][q["pack_idx"][q["msg_send_off"][j]:q["msg_send_off"][j] + cnt]]
+            for n in "x y z xd yd zd nodalMass".split():
+                assert np.array_equal(out[r][n][mine], out[peer][n][theirs]), (r, peer, n)
+
+
+def test_eight_ranks_against_reference_golden(lb, goldens):
+    """2x2x2 ranks of 10^3 == the reference's -s 20 run (575 cycles)."""
+    if ngpu() < 8:
+        pytest.skip("needs 8 GPUs")
+    gold = goldens["lulesh_omp -s 20"]
+    out = run_ranks(lb, (2, 2, 2), (10, 10, 10), 9999999)
+    assert out[0]["s"].cycle == gold["cycles"]
+    assert abs(out[0]["e"][0] - gold["e0"]) <= 1e-8 * gold["e0"]
+
+
+def test_two_rank_driver_binary(lb, goldens):
+    if ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = subprocess.run([lb.BIN_PATH, "--gpus", "2", "--global", "20"], capture_output=True, text=True,
+                       env={"LULESH_B200_FULL_PRECISION": "1", "PATH": "/usr/bin:/bin"})
+    assert p.returncode == 0, p.stderr + p.stdout
+    assert "Num processors: 2" in p.stdout and "   MPI tasks           =  2\n" in p.stdout
+    rec = json.loads([l for l in p.stdout.splitlines() if l.startswith("B200JSON ")][0][9:])
+    gold = goldens["lulesh_omp -s 20"]
+    assert rec["cycles"] == gold["cycles"]
+    assert abs(rec["e0"] - gold["e0"]) <= 1e-8 * gold["e0"]
