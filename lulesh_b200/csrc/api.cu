@@ -388,28 +388,58 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    for (int i = 0; i < v->numSymmY; ++i) nodeFlags[v->symmY[i]] |= NODE_SYMM_Y;
    for (int i = 0; i < v->numSymmZ; ++i) nodeFlags[v->symmZ[i]] |= NODE_SYMM_Z;
 
-   // ---- region work list: regions ordered by descending rep (heaviest blocks are
-   // scheduled first), each padded to whole blocks so rep is block-uniform
+   // ---- region work list.  Every region is padded to whole blocks so that the EOS
+   // repetition count is block-uniform (no divergence in the rep loop).  Block order:
+   // the blocks of the most expensive repetition class are FP64-bound, the cheap ones are
+   // bound by their three dependent gathers; interleaving them lets each SM overlap the
+   // two, and the expensive blocks are all issued within the first ~3/4 of the grid so
+   // that they never form the tail.
    {
+      struct Block { int first, rep; };
+      std::vector<int> entries;
+      std::vector<Block> heavy, light;
+      long long total = 0;
+      int max_rep = 0, min_rep = INT_MAX;
+      for (int r = 0; r < v->numReg; ++r) {
+         const int rep = region_rep(r, v->numReg, v->cost);
+         if (v->regElemSize[r] > 0) { max_rep = std::max(max_rep, rep); min_rep = std::min(min_rep, rep); }
+      }
       std::vector<int> order(v->numReg);
       for (int r = 0; r < v->numReg; ++r) order[r] = r;
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
          return region_rep(a, v->numReg, v->cost) > region_rep(b, v->numReg, v->cost);
       });
-      std::vector<int> work, reps;
-      long long total = 0;
       for (int r : order) {
-         const int n = v->regElemSize[r];
+         const int n = v->regElemSize[r], rep = region_rep(r, v->numReg, v->cost);
          total += n;
-         for (int t = 0; t < n; ++t) {
-            const int el = v->regElemlist[r][t];
-            if (el < 0 || el >= ne) return fail(LULESH_B200_EINVAL, "region list entry out of range");
-            work.push_back(el);
+         for (int t0 = 0; t0 < n; t0 += MAT_THREADS) {
+            Block b{(int)entries.size(), rep};
+            for (int t = t0; t < t0 + MAT_THREADS; ++t) {
+               int el = -1;
+               if (t < n) {
+                  el = v->regElemlist[r][t];
+                  if (el < 0 || el >= ne) return fail(LULESH_B200_EINVAL, "region list entry out of range");
+               }
+               entries.push_back(el);
+            }
+            ((rep == max_rep && max_rep > min_rep) ? heavy : light).push_back(b);
          }
-         while (work.size() % MAT_THREADS) work.push_back(-1);
-         reps.resize(work.size() / MAT_THREADS, region_rep(r, v->numReg, v->cost));
       }
       if (total != ne) return fail(LULESH_B200_EINVAL, "region lists cover %lld of %d elements", total, ne);
+      std::vector<Block> sched;
+      size_t li = 0;
+      for (size_t hi = 0; hi < heavy.size(); ++hi) {
+         sched.push_back(heavy[hi]);
+         const size_t upto = (size_t)((double)(hi + 1) * 0.75 * (double)light.size() / (double)heavy.size());
+         while (li < upto && li < light.size()) sched.push_back(light[li++]);
+      }
+      while (li < light.size()) sched.push_back(light[li++]);
+      std::vector<int> work, reps;
+      work.reserve(entries.size());
+      for (const Block &b : sched) {
+         work.insert(work.end(), entries.begin() + b.first, entries.begin() + b.first + MAT_THREADS);
+         reps.push_back(b.rep);
+      }
       int *p_;
       if ((rc = dev_upload(h, &p_, work.data(), work.size()))) return rc;
       P.workElem = p_;
