@@ -118,6 +118,7 @@ struct lulesh_b200 {
    int numRanks = 1, rank = 0;
    cudaStream_t stream = nullptr, comm_stream = nullptr;
    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+   cudaEvent_t ev_fork = nullptr, ev_dt = nullptr;
    KParams P{};
    Ctl *h_ctl = nullptr;   // pinned mirror
    std::vector<void *> allocs;
@@ -140,6 +141,7 @@ struct lulesh_b200 {
    int *mq_idx = nullptr;
    size_t mq_total = 0;
    int64_t launches = 0;
+   int launches_per_cycle = 5;
    int k1_grid = 0, k3_grid = 0;   // persistent grids: SMs x resident blocks (capped by the work)
 };
 
@@ -283,6 +285,8 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
    CK(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
    CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+   CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+   CK(cudaEventCreateWithFlags(&h->ev_dt, cudaEventDisableTiming));
    CK(cudaEventCreate(&h->ev_t0));
    CK(cudaEventCreate(&h->ev_t1));
    CK(cudaMallocHost(&h->h_ctl, sizeof(Ctl)));
@@ -656,6 +660,8 @@ extern "C" void lulesh_b200_destroy(lulesh_b200 *h)
    if (h->h_ctl) cudaFreeHost(h->h_ctl);
    if (h->ev_a) cudaEventDestroy(h->ev_a);
    if (h->ev_b) cudaEventDestroy(h->ev_b);
+   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+   if (h->ev_dt) cudaEventDestroy(h->ev_dt);
    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
    if (h->stream) cudaStreamDestroy(h->stream);
@@ -715,12 +721,21 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
    cudaStream_t s = h->stream;
    const int dbg = h->debug;
    if (marks) CK(cudaEventRecord(marks[0], s));
+   // K1 does not use dt (only K2/K3 do, lulesh.cc:1230,1577), so at several ranks the
+   // TimeIncrement chain with its min-allreduce runs on the comm stream underneath K1.
+   const bool overlap_dt = (h->numRanks > 1) && !marks;
    if (h->numRanks == 1) {
       k_time_increment<<<1, 32, 0, s>>>(P.ctl, 0);
    } else {
-      k_time_increment<<<1, 32, 0, s>>>(P.ctl, 1);
-      NK(h->nccl->AllReduce(&P.ctl->gnewdt, &P.ctl->gnewdt, 1, ncclDouble, ncclMin, h->comm, s));
-      k_time_increment<<<1, 32, 0, s>>>(P.ctl, 2);
+      cudaStream_t ts = overlap_dt ? h->comm_stream : s;
+      if (overlap_dt) {
+         CK(cudaEventRecord(h->ev_fork, s));
+         CK(cudaStreamWaitEvent(ts, h->ev_fork, 0));
+      }
+      k_time_increment<<<1, 32, 0, ts>>>(P.ctl, 1);
+      NK(h->nccl->AllReduce(&P.ctl->gnewdt, &P.ctl->gnewdt, 1, ncclDouble, ncclMin, h->comm, ts));
+      k_time_increment<<<1, 32, 0, ts>>>(P.ctl, 2);
+      if (overlap_dt) CK(cudaEventRecord(h->ev_dt, ts));
       h->launches += 2;
    }
    if (marks) CK(cudaEventRecord(marks[1], s));
@@ -730,6 +745,7 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
       int rc;
       k_node_boundary_gather<<<blocks_for(P.nbnode, 128), 128, 0, s>>>(P);
       if ((rc = exchange_nodes(h))) return rc;
+      if (overlap_dt) CK(cudaStreamWaitEvent(s, h->ev_dt, 0));
       k_node<<<blocks_for(P.nn, K2_THREADS), K2_THREADS, 0, s>>>(P, dbg);   // interior, overlaps the exchange
       CK(cudaStreamWaitEvent(s, h->ev_b, 0));
       k_node_boundary_update<<<blocks_for(P.nbnode, 128), 128, 0, s>>>(P, dbg);
@@ -761,6 +777,7 @@ static int ensure_graph(lulesh_b200 *h)
    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
    int rc = enqueue_cycle(h, nullptr);
    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+   h->launches_per_cycle = (int)(h->launches - saved);
    h->launches = saved;
    if (rc) return rc;
    if (e != cudaSuccess) return fail(LULESH_B200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -772,8 +789,14 @@ static int ensure_graph(lulesh_b200 *h)
 
 static bool use_graph(const lulesh_b200 *h)
 {
+   // At one rank a cycle (5 kernels) is captured once and replayed.  The multi-rank cycle
+   // (two streams + NCCL operations) is launched eagerly by default: NCCL 2.28 reported an
+   // internal error when its first collective was issued under capture on the forked
+   // stream; LULESH_B200_MULTI_GRAPH=1 opts in for experiments.
    static const bool disabled = getenv("LULESH_B200_NO_GRAPH") != nullptr;
-   return h->numRanks == 1 && !disabled;
+   static const bool multi_enabled = getenv("LULESH_B200_MULTI_GRAPH") != nullptr;
+   if (disabled) return false;
+   return h->numRanks == 1 || multi_enabled;
 }
 
 static int enqueue_cycles(lulesh_b200 *h, int n)
@@ -782,7 +805,7 @@ static int enqueue_cycles(lulesh_b200 *h, int n)
    if (use_graph(h)) {
       if ((rc = ensure_graph(h))) return rc;
       for (int i = 0; i < n; ++i) CK(cudaGraphLaunch(h->graph, h->stream));
-      h->launches += (int64_t)5 * n;
+      h->launches += (int64_t)h->launches_per_cycle * n;
    } else {
       for (int i = 0; i < n; ++i)
          if ((rc = enqueue_cycle(h, nullptr))) return rc;
