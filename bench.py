@@ -221,6 +221,7 @@ def main():
     barrier()
     clocks = sampler.stop() if sampler else None
     value = ne_total * args.steps / (ms * 1e-3)
+    halo_mode = dev.halo_mode
 
     # ---------------- per-kernel times, live, CUDA events on the launching stream
     pk_cycles = min(args.steps, 50)
@@ -307,7 +308,7 @@ def main():
         "metric": "LULESH FOM (zone-cycles/s)", "value": value, "unit": "zones/s", "n_gpus": n,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, n),
+        "data": "synthetic", "config": dict(workload_config(args, n), halo=halo_mode),
         "fom_reference_units": value / 1000.0,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         "clocks": clocks,

@@ -230,6 +230,10 @@ int lulesh_b200_halo_plan_query(const lulesh_b200_halo_plan *plan, const char *w
                                 const int32_t **data, size_t *count);
 void lulesh_b200_halo_plan_destroy(lulesh_b200_halo_plan *plan);
 
+/* "none" (1 rank), "p2p" (NVLink peer stores + flags) or "nccl" (send/recv fallback;
+ * forced with LULESH_B200_HALO=nccl). */
+const char *lulesh_b200_halo_mode(lulesh_b200 *h);
+
 const char *lulesh_b200_last_error(void);
 
 /* Replaces ~Domain (lulesh-init.cc:198-213) for the device side. */

@@ -84,7 +84,7 @@ ABI_SYMBOLS = (
     "lulesh_b200_upload lulesh_b200_field_count lulesh_b200_set_debug "
     "lulesh_b200_kernel_time_increment lulesh_b200_kernel_force lulesh_b200_kernel_node "
     "lulesh_b200_kernel_kinematics lulesh_b200_kernel_material lulesh_b200_time_cycles "
-    "lulesh_b200_device_bytes lulesh_b200_upload_bytes lulesh_b200_last_error "
+    "lulesh_b200_device_bytes lulesh_b200_upload_bytes lulesh_b200_last_error lulesh_b200_halo_mode "
     "lulesh_b200_halo_plan_create lulesh_b200_halo_plan_query lulesh_b200_halo_plan_destroy "
     "lulesh_b200_destroy "
     "lulesh_host_domain_new lulesh_host_domain_free lulesh_host_domain_view "
@@ -119,6 +119,7 @@ _sig("lulesh_b200_time_cycles", C.c_int, _vp, C.c_int32, C.POINTER(C.c_float),
 _sig("lulesh_b200_device_bytes", C.c_size_t, _vp)
 _sig("lulesh_b200_upload_bytes", C.c_size_t, _vp)
 _sig("lulesh_b200_last_error", C.c_char_p)
+_sig("lulesh_b200_halo_mode", C.c_char_p, _vp)
 _sig("lulesh_b200_destroy", None, _vp)
 _sig("lulesh_b200_halo_plan_create", C.c_int, C.POINTER(HostView), C.POINTER(_vp))
 _sig("lulesh_b200_halo_plan_query", C.c_int, _vp, C.c_char_p, C.POINTER(_pi), C.POINTER(C.c_size_t))
@@ -300,6 +301,7 @@ class Device:
         self._check(rc, "time_cycles")
         return total.value, (list(pk) if per_kernel else None), launches.value
 
+    halo_mode = property(lambda s: _lib.lulesh_b200_halo_mode(s._h).decode())
     device_bytes = property(lambda s: _lib.lulesh_b200_device_bytes(s._h))
     upload_bytes = property(lambda s: _lib.lulesh_b200_upload_bytes(s._h))
 

@@ -7,6 +7,7 @@
 // device every compute entry point returns LULESH_B200_ECUDA.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>   // types only; every NCCL symbol is resolved with dlsym at run time
 
 #include <algorithm>
@@ -63,6 +64,7 @@ struct NcclApi {
    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                              cudaStream_t) = nullptr;
    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+   ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 };
 
 static NcclApi *nccl_api()
@@ -87,6 +89,7 @@ static NcclApi *nccl_api()
    SYM(Recv, "ncclRecv")
    SYM(AllReduce, "ncclAllReduce")
    SYM(GetErrorString, "ncclGetErrorString")
+   SYM(AllGather, "ncclAllGather")
 #undef SYM
    return &api;
 }
@@ -141,6 +144,18 @@ struct lulesh_b200 {
    int *mq_idx = nullptr;
    size_t mq_total = 0;
    int64_t launches = 0;
+   // peer-to-peer exchange state (numRanks > 1 and every rank can map every other rank's arena)
+   bool p2p = false;
+   char *arena = nullptr;            // one allocation: flags | dt slots | fhalo[2] | delv[3][allElem]
+   size_t arena_bytes = 0;
+   unsigned long long *flags = nullptr;
+   DtSlot *dtslots = nullptr;
+   PeerCounters *counters = nullptr;
+   PeerMsg *d_node_msgs = nullptr, *d_face_msgs = nullptr;
+   unsigned char *d_node_slot_msg = nullptr, *d_face_slot_msg = nullptr;
+   DtSlot **d_peer_slots = nullptr;
+   std::vector<void *> ipc_opened;
+   std::string halo_mode = "none";
    int launches_per_cycle = 5;
    int k1_grid = 0, k3_grid = 0;   // persistent grids: SMs x resident blocks (capped by the work)
 };
@@ -349,15 +364,14 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    ZERO_ELEM(LULESH_F_DELX_XI, P.delx_xi, ne) ZERO_ELEM(LULESH_F_DELX_ETA, P.delx_eta, ne)
    ZERO_ELEM(LULESH_F_DELX_ZETA, P.delx_zeta, ne)
 #undef ZERO_ELEM
-   {  // delv_xi/eta/zeta share one allocation [3][allElem] (ghost blocks at the tail of each)
+   if (v->numRanks == 1) {
+      // delv_xi/eta/zeta share one allocation [3][allElem] (ghost blocks at the tail of each);
+      // at several ranks they live in the peer-visible arena allocated by build_comm()
       double *g;
       if ((rc = dev_zero(h, &g, (size_t)3 * P.allElem))) return rc;
       P.delv_xi = g; P.delv_eta = g + P.allElem; P.delv_zeta = g + 2 * (size_t)P.allElem;
-      for (int a = 0; a < 3; ++a) {
-         h->field_ptr[LULESH_F_DELV_XI + a] = g + (size_t)a * P.allElem;
-         h->field_cnt[LULESH_F_DELV_XI + a] = P.allElem;
-      }
    }
+   for (int a = 0; a < 3; ++a) h->field_cnt[LULESH_F_DELV_XI + a] = P.allElem;
    {
       int *p_;
 #define UP_INT(name, cnt) if ((rc = dev_upload(h, &p_, v->name, (size_t)(cnt)))) return rc; P.name = p_;
@@ -455,6 +469,7 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    if (v->numRanks > 1) {
       if ((rc = build_comm(h, v, unique_id, nodeFlags))) return rc;
    }
+   for (int a = 0; a < 3; ++a) h->field_ptr[LULESH_F_DELV_XI + a] = P.delv_xi + (size_t)a * P.allElem;
    {
       unsigned char *p_;
       if ((rc = dev_upload(h, &p_, nodeFlags.data(), nodeFlags.size()))) return rc;
@@ -598,6 +613,145 @@ extern "C" int lulesh_b200_halo_plan_query(const lulesh_b200_halo_plan *pl, cons
 
 extern "C" void lulesh_b200_halo_plan_destroy(lulesh_b200_halo_plan *pl) { delete pl; }
 
+// --------------------------------------------------------------------------
+// Peer-to-peer setup: every rank publishes where its receive slots live (one table per
+// rank, all-gathered over NCCL), maps the other ranks' arenas (raw pointers + peer access
+// inside one process, CUDA IPC handles across processes) and builds the device tables the
+// exchange kernels use.  All ranks then agree (min-allreduce of a flag) on whether the
+// peer path is usable; otherwise everybody stays on NCCL send/recv.
+// --------------------------------------------------------------------------
+struct PeerTable {
+   int pid, device, rank, nmsg, nface, allElem, fhalo_size, ok;
+   unsigned long long base;          // arena address in the owner's address space
+   unsigned long long alloc_off;     // arena offset inside the cudaMalloc block the IPC handle names
+   cudaIpcMemHandle_t handle;
+   int msg_rank[26], msg_recv_off[26];
+   int face_rank[6], face_ghost_off[6];
+   unsigned long long off_fhalo, off_delv;
+};
+
+static int setup_p2p(lulesh_b200 *h, const lulesh_b200_host_view *v, const lulesh_b200_halo_plan &pl)
+{
+   KParams &P = h->P;
+   const int n = v->numRanks, me = v->rank;
+   const char *mode = getenv("LULESH_B200_HALO");
+   const bool want = !(mode && !strcmp(mode, "nccl")) && n <= PEER_MAX_RANKS && h->nccl->AllGather;
+   int rc;
+
+   PeerTable mine;
+   memset(&mine, 0, sizeof mine);
+   mine.pid = (int)getpid(); mine.device = h->device; mine.rank = me;
+   mine.nmsg = (int)pl.msg_rank.size(); mine.nface = (int)pl.face_rank.size();
+   mine.allElem = P.allElem; mine.fhalo_size = pl.fhalo_size; mine.ok = want ? 1 : 0;
+   mine.base = (unsigned long long)(uintptr_t)h->arena;
+   mine.off_fhalo = (unsigned long long)((char *)P.fhalo - h->arena);
+   mine.off_delv = (unsigned long long)((char *)P.delv_xi - h->arena);
+   for (int i = 0; i < mine.nmsg; ++i) { mine.msg_rank[i] = pl.msg_rank[i]; mine.msg_recv_off[i] = pl.msg_recv_off[i]; }
+   for (int i = 0; i < mine.nface; ++i) { mine.face_rank[i] = pl.face_rank[i]; mine.face_ghost_off[i] = pl.face_ghost_off[i]; }
+   if (want) {
+      if (cudaIpcGetMemHandle(&mine.handle, h->arena) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+      // the handle names the whole cudaMalloc block; find the arena's offset inside it
+      typedef int (*GetRange)(unsigned long long *, size_t *, unsigned long long);
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      unsigned long long blockBase = mine.base;
+      if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) == cudaSuccess && fn) {
+         size_t sz = 0;
+         if (((GetRange)fn)(&blockBase, &sz, mine.base) != 0) blockBase = mine.base;
+      } else cudaGetLastError();
+      mine.alloc_off = mine.base - blockBase;
+   }
+
+   // all-gather the tables
+   std::vector<PeerTable> all(n);
+   PeerTable *d_tab = nullptr;
+   if ((rc = dev_zero(h, &d_tab, (size_t)n))) return rc;
+   CK(cudaMemcpy(d_tab + me, &mine, sizeof mine, cudaMemcpyHostToDevice));
+   if (h->nccl->AllGather) {
+      NK(h->nccl->AllGather(d_tab + me, d_tab, sizeof(PeerTable), ncclChar, h->comm, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      CK(cudaMemcpy(all.data(), d_tab, sizeof(PeerTable) * n, cudaMemcpyDeviceToHost));
+   } else all[me] = mine;
+
+   // map every other rank's arena
+   std::vector<char *> peer_arena(n, nullptr);
+   int ok = want ? 1 : 0;
+   for (int r = 0; r < n && ok; ++r) ok = all[r].ok;
+   for (int r = 0; r < n && ok; ++r) {
+      if (r == me) { peer_arena[r] = h->arena; continue; }
+      if (all[r].pid == mine.pid) {
+         int can = 0;
+         if (cudaDeviceCanAccessPeer(&can, h->device, all[r].device) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+         cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; }
+         cudaGetLastError();
+         peer_arena[r] = (char *)(uintptr_t)all[r].base;
+      } else {
+         void *blk = nullptr;
+         if (cudaIpcOpenMemHandle(&blk, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError(); ok = 0; break;
+         }
+         h->ipc_opened.push_back(blk);
+         peer_arena[r] = (char *)blk + all[r].alloc_off;
+      }
+   }
+
+   // every rank must take the same path
+   int *d_ok = nullptr;
+   if ((rc = dev_zero(h, &d_ok, 1))) return rc;
+   CK(cudaMemcpy(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice));
+   NK(h->nccl->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
+   CK(cudaStreamSynchronize(h->stream));
+   CK(cudaMemcpy(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost));
+   if (!ok) return 0;   // stay on NCCL send/recv
+
+   // device tables
+   std::vector<PeerMsg> node_msgs, face_msgs;
+   std::vector<unsigned char> node_slot, face_slot;
+   for (int i = 0; i < mine.nmsg; ++i) {
+      const int r = pl.msg_rank[i];
+      int j = -1;
+      for (int t = 0; t < all[r].nmsg; ++t) if (all[r].msg_rank[t] == me) j = t;
+      if (j < 0) return fail(LULESH_B200_EINVAL, "rank %d does not list rank %d as a neighbour", r, me);
+      PeerMsg m;
+      m.dst = reinterpret_cast<double *>(peer_arena[r] + all[r].off_fhalo) + all[r].msg_recv_off[j];
+      m.flag = reinterpret_cast<unsigned long long *>(peer_arena[r]) + PEER_FLAG_NODE + j;
+      m.send_off = pl.msg_send_off[i]; m.count = pl.msg_count[i];
+      m.field_stride = pl.msg_count[i]; m.parity_stride = all[r].fhalo_size;
+      node_msgs.push_back(m);
+      node_slot.insert(node_slot.end(), (size_t)3 * m.count, (unsigned char)i);
+   }
+   for (int i = 0; i < mine.nface; ++i) {
+      const int r = pl.face_rank[i];
+      int j = -1;
+      for (int t = 0; t < all[r].nface; ++t) if (all[r].face_rank[t] == me) j = t;
+      if (j < 0) return fail(LULESH_B200_EINVAL, "rank %d does not list rank %d as a face neighbour", r, me);
+      PeerMsg m;
+      m.dst = reinterpret_cast<double *>(peer_arena[r] + all[r].off_delv) + all[r].face_ghost_off[j];
+      m.flag = reinterpret_cast<unsigned long long *>(peer_arena[r]) + PEER_FLAG_FACE + j;
+      m.send_off = pl.face_send_off[i]; m.count = pl.face_count[i];
+      m.field_stride = all[r].allElem; m.parity_stride = 0;
+      face_msgs.push_back(m);
+      face_slot.insert(face_slot.end(), (size_t)3 * m.count, (unsigned char)i);
+   }
+   std::vector<DtSlot *> slots(n);
+   for (int r = 0; r < n; ++r)
+      slots[r] = reinterpret_cast<DtSlot *>(peer_arena[r] + PEER_NUM_FLAGS * sizeof(unsigned long long));
+   if ((rc = dev_upload(h, &h->d_node_msgs, node_msgs.data(), node_msgs.size()))) return rc;
+   if ((rc = dev_upload(h, &h->d_face_msgs, face_msgs.data(), face_msgs.size()))) return rc;
+   if ((rc = dev_upload(h, &h->d_node_slot_msg, node_slot.data(), node_slot.size()))) return rc;
+   if ((rc = dev_upload(h, &h->d_face_slot_msg, face_slot.data(), face_slot.size()))) return rc;
+   if ((rc = dev_upload(h, &h->d_peer_slots, slots.data(), slots.size()))) return rc;
+   if ((rc = dev_zero(h, &h->counters, 1))) return rc;
+   P.peer_cnt = h->counters;
+   h->p2p = true;
+   h->halo_mode = "p2p";
+   // nobody may start writing into a peer before that peer has finished zeroing its arena
+   NK(h->nccl->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
+   CK(cudaStreamSynchronize(h->stream));
+   return 0;
+}
+
 static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void *unique_id,
                       std::vector<unsigned char> &nodeFlags)
 {
@@ -626,7 +780,19 @@ static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void
    if ((rc = dev_upload(h, &pi, pl.bsum_src.data(), pl.bsum_src.size()))) return rc;
    P.bsum_src = pi;
    if ((rc = dev_upload(h, &h->pack_idx, pl.pack_idx.data(), pl.pack_idx.size()))) return rc;
-   if ((rc = dev_zero(h, &P.fhalo, (size_t)pl.fhalo_size))) return rc;
+   {  // peer-visible arena: flags | dt slots | fhalo[2] (double-buffered by sequence parity) | delv
+      const size_t off_fhalo = 4096;
+      const size_t fhalo_bytes = (((size_t)2 * pl.fhalo_size * sizeof(double)) + 255) & ~(size_t)255;
+      const size_t off_delv = off_fhalo + fhalo_bytes;
+      h->arena_bytes = off_delv + (size_t)3 * P.allElem * sizeof(double);
+      if ((rc = dev_zero(h, &h->arena, h->arena_bytes))) return rc;
+      h->flags = reinterpret_cast<unsigned long long *>(h->arena);
+      h->dtslots = reinterpret_cast<DtSlot *>(h->arena + PEER_NUM_FLAGS * sizeof(unsigned long long));
+      static_assert(PEER_NUM_FLAGS * 8 + 2 * PEER_MAX_RANKS * sizeof(DtSlot) <= 4096, "arena header");
+      P.fhalo = reinterpret_cast<double *>(h->arena + off_fhalo);
+      double *g = reinterpret_cast<double *>(h->arena + off_delv);
+      P.delv_xi = g; P.delv_eta = g + P.allElem; P.delv_zeta = g + 2 * (size_t)P.allElem;
+   }
    if ((rc = dev_zero(h, &h->sendbuf, (size_t)pl.send_total))) return rc;
    if ((rc = dev_upload(h, &h->mq_idx, pl.mq_idx.data(), pl.mq_idx.size()))) return rc;
    if ((rc = dev_zero(h, &h->mq_send, (size_t)pl.mq_total))) return rc;
@@ -634,7 +800,8 @@ static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void
    ncclUniqueId id;
    memcpy(&id, unique_id, sizeof id);
    NK(h->nccl->CommInitRank(&h->comm, v->numRanks, id, v->rank));
-   return 0;
+   h->halo_mode = "nccl";
+   return setup_p2p(h, v, pl);
 }
 
 extern "C" int lulesh_b200_create(const lulesh_b200_host_view *view, int device,
@@ -656,6 +823,7 @@ extern "C" void lulesh_b200_destroy(lulesh_b200 *h)
    if (h->stream) cudaStreamSynchronize(h->stream);
    if (h->comm && h->nccl) h->nccl->CommDestroy(h->comm);
    if (h->graph) cudaGraphExecDestroy(h->graph);
+   for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
    for (void *p : h->allocs) cudaFree(p);
    if (h->h_ctl) cudaFreeHost(h->h_ctl);
    if (h->ev_a) cudaEventDestroy(h->ev_a);
@@ -732,8 +900,14 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
          CK(cudaEventRecord(h->ev_fork, s));
          CK(cudaStreamWaitEvent(ts, h->ev_fork, 0));
       }
-      k_time_increment<<<1, 32, 0, ts>>>(P.ctl, 1);
-      NK(h->nccl->AllReduce(&P.ctl->gnewdt, &P.ctl->gnewdt, 1, ncclDouble, ncclMin, h->comm, ts));
+      if (h->p2p) {   // candidates are written into every rank's slot table over NVLink
+         k_peer_dt_post<<<1, PEER_MAX_RANKS, 0, ts>>>(P.ctl, h->d_peer_slots, h->rank, h->numRanks,
+                                                      &h->counters->dt_seq);
+         k_peer_dt_wait<<<1, PEER_MAX_RANKS, 0, ts>>>(P.ctl, h->dtslots, h->numRanks, &h->counters->dt_expect);
+      } else {
+         k_time_increment<<<1, 32, 0, ts>>>(P.ctl, 1);
+         NK(h->nccl->AllReduce(&P.ctl->gnewdt, &P.ctl->gnewdt, 1, ncclDouble, ncclMin, h->comm, ts));
+      }
       k_time_increment<<<1, 32, 0, ts>>>(P.ctl, 2);
       if (overlap_dt) CK(cudaEventRecord(h->ev_dt, ts));
       h->launches += 2;
@@ -741,7 +915,29 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
    if (marks) CK(cudaEventRecord(marks[1], s));
    k_force<<<h->k1_grid, K1_THREADS, K1_SMEM_BYTES, s>>>(P);
    if (marks) CK(cudaEventRecord(marks[2], s));
-   if (h->numRanks > 1) {
+   if (h->numRanks > 1 && h->p2p) {
+      // Shared nodes: gather own partials -> store them into the neighbours -> wait for theirs ->
+      // sum in rank order and advance.  The whole chain runs on the comm stream underneath the
+      // interior node update (it follows the dt chain there, which boundary_update needs anyway).
+      cudaStream_t bs = overlap_dt ? h->comm_stream : s;
+      if (overlap_dt) {
+         CK(cudaEventRecord(h->ev_a, s));                 // K1 finished
+         CK(cudaStreamWaitEvent(bs, h->ev_a, 0));
+      }
+      k_node_boundary_gather<<<blocks_for(P.nbnode, 128), 128, 0, bs>>>(P);
+      k_peer_pack<<<blocks_for((int)h->send_total, 256), 256, 0, bs>>>(
+         P.fhalo, P.fhalo_stride, h->pack_idx, h->d_node_slot_msg, (int)h->send_total, h->d_node_msgs,
+         (int)h->msgs.size(), &h->counters->node_done, &h->counters->node_seq);
+      k_peer_wait<<<1, 32, 0, bs>>>(h->flags, PEER_FLAG_NODE, (int)h->msgs.size(), &h->counters->node_expect, P.ctl);
+      k_node_boundary_update<<<blocks_for(P.nbnode, 128), 128, 0, bs>>>(P, dbg);
+      if (overlap_dt) {
+         CK(cudaEventRecord(h->ev_b, bs));
+         CK(cudaStreamWaitEvent(s, h->ev_dt, 0));
+      }
+      k_node<<<blocks_for(P.nn, K2_THREADS), K2_THREADS, 0, s>>>(P, dbg);   // interior nodes
+      if (overlap_dt) CK(cudaStreamWaitEvent(s, h->ev_b, 0));
+      h->launches += 4;
+   } else if (h->numRanks > 1) {
       int rc;
       k_node_boundary_gather<<<blocks_for(P.nbnode, 128), 128, 0, s>>>(P);
       if ((rc = exchange_nodes(h))) return rc;
@@ -755,7 +951,13 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
    }
    if (marks) CK(cudaEventRecord(marks[3], s));
    k_kinematics<<<h->k3_grid, K3_THREADS, K3_SMEM_BYTES, s>>>(P);
-   if (h->numRanks > 1) {
+   if (h->numRanks > 1 && h->p2p) {
+      k_peer_pack<<<blocks_for((int)h->mq_total, 256), 256, 0, s>>>(
+         P.delv_xi, 0, h->mq_idx, h->d_face_slot_msg, (int)h->mq_total, h->d_face_msgs,
+         (int)h->faces.size(), &h->counters->face_done, &h->counters->face_seq);
+      k_peer_wait<<<1, 32, 0, s>>>(h->flags, PEER_FLAG_FACE, (int)h->faces.size(), &h->counters->face_expect, P.ctl);
+      h->launches += 2;
+   } else if (h->numRanks > 1) {
       int rc;
       if ((rc = exchange_monoq(h))) return rc;
       h->launches += 1;
@@ -789,14 +991,14 @@ static int ensure_graph(lulesh_b200 *h)
 
 static bool use_graph(const lulesh_b200 *h)
 {
-   // At one rank a cycle (5 kernels) is captured once and replayed.  The multi-rank cycle
-   // (two streams + NCCL operations) is launched eagerly by default: NCCL 2.28 reported an
-   // internal error when its first collective was issued under capture on the forked
-   // stream; LULESH_B200_MULTI_GRAPH=1 opts in for experiments.
+   // A cycle is captured once and replayed: 5 kernels at one rank; kernels + peer-to-peer
+   // exchange kernels on two streams at several ranks.  With the NCCL fallback the cycle is
+   // launched eagerly (NCCL 2.28 reported an internal error when its first collective was
+   // issued under capture on the forked stream; LULESH_B200_MULTI_GRAPH=1 opts in).
    static const bool disabled = getenv("LULESH_B200_NO_GRAPH") != nullptr;
    static const bool multi_enabled = getenv("LULESH_B200_MULTI_GRAPH") != nullptr;
    if (disabled) return false;
-   return h->numRanks == 1 || multi_enabled;
+   return h->numRanks == 1 || h->p2p || multi_enabled;
 }
 
 static int enqueue_cycles(lulesh_b200 *h, int n)
@@ -1039,5 +1241,6 @@ extern "C" int lulesh_b200_kernel_material(lulesh_b200 *h)
    return finish_kernel(h);
 }
 
+extern "C" const char *lulesh_b200_halo_mode(lulesh_b200 *h) { return h ? h->halo_mode.c_str() : ""; }
 extern "C" size_t lulesh_b200_device_bytes(lulesh_b200 *h) { return h ? h->device_bytes : 0; }
 extern "C" size_t lulesh_b200_upload_bytes(lulesh_b200 *h) { return h ? h->upload_bytes : 0; }

@@ -73,6 +73,7 @@ struct KParams {
    const int *bsum_src;           // index into fhalo planes (own slot or recv slot)
    double *fhalo;                 // [3][fhalo_stride]: own partials [0,nbnode) then recv slots
    int fhalo_stride;
+   const struct PeerCounters *peer_cnt;   // non-null in peer-to-peer mode: fhalo is double-buffered by sequence parity
    int unit_rho0;                 // refdens == 1.0: EOS skips the exact no-op division
    lulesh_b200_constants c;
 };
@@ -106,6 +107,37 @@ __global__ void k_node_boundary_update(const KParams P, int storeDebug);
 __global__ void k_kinematics(const KParams P);
 __global__ void k_material(const KParams P, int storeQ);
 __global__ void k_gather_index(double *dst, const double *src, const int *idx, int n);
+
+// ---- peer-to-peer halo exchange over NVLink (stores into the neighbour's HBM + flags)
+constexpr int PEER_MAX_RANKS = 64;
+constexpr int PEER_FLAG_NODE = 0;     // flags[0..25]: node-halo messages, receiver's message index
+constexpr int PEER_FLAG_FACE = 32;    // flags[32..37]: MonoQ face messages, receiver's face index
+constexpr int PEER_NUM_FLAGS = 64;
+
+struct DtSlot { double val; unsigned long long seq; };
+
+struct PeerMsg {                       // one outgoing message
+   double *dst;                        // peer memory: where field 0 of this message starts
+   unsigned long long *flag;           // peer memory: the receiver's flag for this message
+   int send_off, count;                // slot range [send_off, send_off + 3*count) of the pack list
+   int field_stride;                   // distance between the three fields at the destination
+   int parity_stride;                  // destination offset of the odd-sequence buffer (0: single buffer)
+};
+
+struct PeerCounters {                  // device-resident sequence numbers, one pair per exchange kind
+   unsigned long long node_seq, node_expect, face_seq, face_expect, dt_seq, dt_expect;
+   unsigned int node_done, face_done;  // "last block" detection of the pack kernels
+};
+
+__global__ void k_peer_pack(const double *src, int src_parity_stride, const int *idx,
+                            const unsigned char *slot_msg, int n, const PeerMsg *msgs, int nmsg,
+                            unsigned int *done_counter, unsigned long long *seq);
+__global__ void k_peer_wait(const unsigned long long *flags, int first, int n,
+                            unsigned long long *expect, Ctl *ctl);
+__global__ void k_peer_dt_post(Ctl *ctl, DtSlot *const *peer_slots, int me, int nranks,
+                               unsigned long long *dt_seq);
+__global__ void k_peer_dt_wait(Ctl *ctl, const DtSlot *my_slots, int nranks,
+                               unsigned long long *dt_expect);
 __global__ void k_boundary_mass(const KParams P, double *nodalMass);
 
 }  // namespace lb200

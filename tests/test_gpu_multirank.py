@@ -17,7 +17,7 @@ def ngpu():
     return torch.cuda.device_count()
 
 
-def run_ranks(lb, decomp, sizes, its, num_reg=11, balance=1, cost=1):
+def run_ranks(lb, decomp, sizes, its, num_reg=11, balance=1, cost=1, expect_mode=None):
     n = decomp[0] * decomp[1] * decomp[2]
     uid = lb.get_unique_id()
     out, errs = [None] * n, []
@@ -27,6 +27,8 @@ def run_ranks(lb, decomp, sizes, its, num_reg=11, balance=1, cost=1):
             dom = lb.Domain(sizes[0], num_reg, balance, cost, num_ranks=n, rank=r, decomp=decomp, sizes=sizes)
             dev = lb.Device(dom, device=r, unique_id=uid)
             dev.sum_nodal_mass()
+            if expect_mode:
+                assert dev.halo_mode == expect_mode, dev.halo_mode
             dev.run(its)
             out[r] = dict(s=dev.scalars, dom=dom,
                           **{f: dev.download(f) for f in "x y z xd yd zd e p q v nodalMass".split()})
@@ -52,13 +54,19 @@ def assemble(out, decomp, sizes, name):
     return g
 
 
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
 @pytest.mark.parametrize("decomp,sizes,need", [((1, 1, 2), (24, 24, 12), 2), ((1, 2, 2), (24, 12, 12), 4),
                                                ((2, 2, 2), (12, 12, 12), 8)])
-def test_ranks_match_single_gpu_global_run(lb, decomp, sizes, need):
+def test_ranks_match_single_gpu_global_run(lb, decomp, sizes, need, halo, monkeypatch):
+    """Both exchange back ends: NVLink peer stores + flags (default) and NCCL send/recv."""
     if ngpu() < need:
         pytest.skip(f"needs {need} GPUs")
+    if halo == "nccl":
+        monkeypatch.setenv("LULESH_B200_HALO", "nccl")
+    else:
+        monkeypatch.delenv("LULESH_B200_HALO", raising=False)
     its = 120
-    out = run_ranks(lb, decomp, sizes, its)
+    out = run_ranks(lb, decomp, sizes, its, expect_mode=halo)
     single = lb.Device(lb.Domain(24))
     single.run(its)
     s1 = single.scalars
