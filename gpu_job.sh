@@ -1,22 +1,20 @@
 mkdir -p gpurun_out
-free -g | head -2 > gpurun_out/host.txt; nproc >> gpurun_out/host.txt; lscpu | grep "Model name" >> gpurun_out/host.txt
-(python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log)
-(timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu_full.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_full.log)
-tail -3 gpurun_out/smoke.log gpurun_out/pytest_gpu_full.log
-python bench.py --impl reference > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err
-python bench.py > gpurun_out/final_s128.json 2> gpurun_out/final_s128.err
-python bench.py --size 256 --steps 60 --warmup 5 > gpurun_out/final_s256.json 2> gpurun_out/final_s256.err
-python bench.py --size 256 --regions 16 --balance 1 --cost 8 --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/final_cfg3.json 2> gpurun_out/final_cfg3.err
-python bench.py --size 320 --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/final_s320.json 2> gpurun_out/final_s320.err
-ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 50 --csv --log-file gpurun_out/final_launches_s128.csv python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_force|k_kinematics|k_material|k_node" -s 40 -c 4 -o gpurun_out/prof_s128_final python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_final.log 2>&1
-ncu --set full --clock-control none -k regex:"k_force|k_kinematics|k_material|k_node" -s 16 -c 4 -o gpurun_out/prof_s256_final python bench.py --size 256 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_final256.log 2>&1
-cat gpurun_out/host.txt
+(timeout 300 python -m pytest tests/test_gpu_multirank.py -m gpu -q --timeout 120 > gpurun_out/pytest_multi_final.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_multi_final.log)
+tail -n 3 gpurun_out/pytest_multi_final.log
+python bench.py --no-cpu-baseline --steps 200 > gpurun_out/scale2_n1.json 2> gpurun_out/scale2_n1.err
+for n in 2 4 8; do
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700+n)) bench.py --gpus $n --steps 200 --no-cpu-baseline > gpurun_out/scale2_n$n.json 2> gpurun_out/scale2_n$n.err
+done
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29750 bench.py --gpus 8 --size 256 --steps 50 --no-cpu-baseline > gpurun_out/scale2_n8_s256.json 2> gpurun_out/scale2_n8_s256.err
+LULESH_B200_HALO=nccl timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29760 bench.py --gpus 8 --steps 200 --no-cpu-baseline > gpurun_out/scale2_n8_nccl.json 2> gpurun_out/scale2_n8_nccl.err
+(timeout 120 ./lulesh_b200/bin/lulesh_b200 --gpus 8 --global 384 -i 100 > gpurun_out/driver_cfg4_8gpu.txt 2>&1; echo "exit $?" >> gpurun_out/driver_cfg4_8gpu.txt)
+(timeout 120 ./lulesh_b200/bin/lulesh_b200 --gpus 1 -s 384 -i 100 > gpurun_out/driver_cfg4_1gpu.txt 2>&1; echo "exit $?" >> gpurun_out/driver_cfg4_1gpu.txt)
+(timeout 300 ./lulesh_b200/bin/lulesh_b200 --gpus 8 -s 320 -i 30 > gpurun_out/driver_cfg5_8gpu.txt 2>&1; echo "exit $?" >> gpurun_out/driver_cfg5_8gpu.txt)
+grep -E "Iteration|Origin|FOM|Elapsed|exit|MPI" gpurun_out/driver_cfg4_8gpu.txt gpurun_out/driver_cfg4_1gpu.txt gpurun_out/driver_cfg5_8gpu.txt
 python - <<'PY'
 import json,glob
-for f in sorted(glob.glob("gpurun_out/final_*.json")):
+for f in sorted(glob.glob("gpurun_out/scale2_n*.json")):
     try:
-        d=json.loads(open(f).read().strip().splitlines()[-1]); r=d.get("roofline") or {}
-        print(f, round(d["value"]/1e9,4), round(d["ms_per_step"],4), {k:round(v,4) for k,v in (r.get("per_kernel_ms") or {}).items()}, "e2e", round(d["e2e"]["value"]/1e9,3), "roof", r.get("kernel"), round(r.get("frac",0),3), "step", round((r.get("step") or {}).get("frac",0),3), d.get("cpu_baseline"))
-    except Exception as e: print(f, "ERR", e, open(f.replace('.json','.err')).read()[-300:])
+        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d["config"].get("halo"), d["n_gpus"], round(d["value"]/1e9,3), round(d["ms_per_step"],4), {k:round(v,4) for k,v in d["roofline"]["per_kernel_ms"].items()}, "e2e", round(d["e2e"]["value"]/1e9,3))
+    except Exception as e: print(f, "ERR", e, open(f.replace('.json','.err')).read()[-400:])
 PY
