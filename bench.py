@@ -64,6 +64,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_ready(self, timeout=8.0):
+        """nvidia-smi start-up (NVML init touches every GPU of the box) must be over before the
+        timed region begins, or it perturbs the lock-stepped multi-GPU cycles."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -150,7 +157,7 @@ def workload_config(args, n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--size", type=int, default=128, help="elements per edge per GPU (-s)")
     ap.add_argument("--regions", type=int, default=11)
@@ -213,9 +220,11 @@ def main():
     # ---------------- device-resident throughput (`value`)
     dev = lb.Device(dom, device=local, unique_id=fresh_uid())
     dev.sum_nodal_mass()
-    dev.time_cycles(args.warmup)
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    dev.time_cycles(args.warmup)
+    if sampler:
+        sampler.wait_ready()
+    barrier()
     ms, _, launches = dev.time_cycles(args.steps)
     ms = allmax(ms)
     barrier()
