@@ -93,25 +93,46 @@ def reference_binary():
     return exe if os.path.exists(exe) else None
 
 
-def run_reference(size, cycles, regions=(11, 1, 1)):
-    """Times the unmodified reference (OpenMP, all host cores) for `cycles` cycles; returns
-    (zone_cycles_per_s, cores, kind, sample).  Falls back to the oracle port if the reference
-    binary did not travel."""
+def run_reference(size, cycles, regions=(11, 1, 1), nranks=1):
+    """Times the unmodified reference on the host cores for `cycles` cycles; returns
+    (zone_cycles_per_s, cores, kind, sample).  nranks == 1: the OpenMP build on all cores.
+    nranks a cube (8, 27): the reference's USE_MPI=1 build, one process per rank, under the
+    single-node MPI stand-in of oracle/mpishim ("MPI+OpenMP -np N"; this image has no MPI).
+    Other rank counts do not exist in the reference (cubic layouts only, lulesh-init.cc:684):
+    the single-domain OpenMP run of the same per-rank size is reported instead.
+    Falls back to the oracle port if the reference binary did not travel."""
     cores = os.cpu_count() or 1
-    env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close", OMP_PLACES="cores")
     r, b, c = regions
     exe, kind = reference_binary(), "reference"
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    cube = round(nranks ** (1.0 / 3.0)) ** 3 == nranks
+    use_mpi = nranks > 1 and cube and os.path.exists(os.path.join(refdir, "lulesh_mpi")) \
+        and os.path.exists(os.path.join(refdir, "mpirun_shim"))
+    threads = max(1, cores // nranks) if use_mpi else cores
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="false" if use_mpi else "close")
+    if use_mpi:
+        env["OMP_WAIT_POLICY"] = "passive"   # ranks x threads == cores: do not spin against each other
+    if not use_mpi:
+        env["OMP_PLACES"] = "cores"
     if exe is None:
         exe, kind = os.path.join(ROOT, "oracle", "_build", "lulesh_oracle"), "port"
         if not os.path.exists(exe):
             subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True)
-    args = [exe, "-s", str(size), "-i", str(cycles), "-r", str(r), "-b", str(b), "-c", str(c)]
-    out = subprocess.run(args, env=env, capture_output=True, text=True, check=True).stdout
+    args = ["-s", str(size), "-i", str(cycles), "-r", str(r), "-b", str(b), "-c", str(c)]
+    if use_mpi:
+        cmd = [os.path.join(refdir, "mpirun_shim"), "-np", str(nranks), os.path.join(refdir, "lulesh_mpi")] + args
+        ranks_done = nranks
+    else:
+        cmd = [exe] + args
+        ranks_done = 1
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, check=True).stdout
     m = re.search(r'"elapsed": ([0-9.eE+-]+)', out)
     n = re.search(r'"cycles": (\d+)', out)
     elapsed, done = float(m.group(1)), int(n.group(1))
-    zcs = float(size) ** 3 * done / elapsed
-    return zcs, cores, kind, f"-s {size} -i {done} -r {r} -b {b} -c {c} ({elapsed:.2f} s, OMP_NUM_THREADS={cores})"
+    zcs = ranks_done * float(size) ** 3 * done / elapsed
+    what = (f"mpirun_shim -np {nranks} lulesh_mpi (reference USE_MPI=1 build), OMP_NUM_THREADS={threads}"
+            if use_mpi else f"lulesh_omp, OMP_NUM_THREADS={threads}")
+    return zcs, cores, kind, f"-s {size} -i {done} -r {r} -b {b} -c {c} ({elapsed:.2f} s, {what})"
 
 
 def reference_cycle_budget(size, steps, seconds=60.0):
@@ -124,20 +145,23 @@ def impl_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cycles = reference_cycle_budget(args.size, args.steps + args.warmup, 120.0)
+    cube = round(args.gpus ** (1.0 / 3.0)) ** 3 == args.gpus
+    nranks = args.gpus if (args.gpus > 1 and cube) else 1
+    cycles = reference_cycle_budget(args.size, args.steps + args.warmup, 120.0 / nranks)
     t0 = time.time()
-    zcs, cores, kind, sample = run_reference(args.size, cycles, (args.regions, args.balance, args.cost))
+    zcs, cores, kind, sample = run_reference(args.size, cycles, (args.regions, args.balance, args.cost), nranks)
     line = {
         "impl": "reference", "metric": "LULESH FOM (zone-cycles/s)", "value": zcs, "unit": "zones/s",
         "n_gpus": args.gpus, "steps": cycles, "warmup": 0,
-        "ms_per_step": 1e3 * float(args.size) ** 3 / zcs, "higher_is_better": True,
+        "ms_per_step": 1e3 * nranks * float(args.size) ** 3 / zcs, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, nranks),
         "cpu_baseline": {"value": zcs, "unit": "zones/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": zcs, "unit": "zones/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.time() - t0,
-        "note": "reference's own OpenMP CPU implementation on the host cores of this box; "
-                "single domain of --size^3 (the MPI build cannot be compiled: no MPI in the image)",
+        "note": "reference's own CPU implementation on the host cores of this box: OpenMP build for one "
+                "domain; for cubic rank counts its USE_MPI=1 build under a single-node MPI stand-in "
+                "(oracle/mpishim; the image has no MPI); 2 and 4 ranks do not exist in the reference",
     }
     print(json.dumps(line), flush=True)
     return 0

@@ -928,6 +928,19 @@ ora_domain *ora_new(int numRanks, int rank, int px, int py, int pz, int sx, int 
    return d;
 }
 
+/* The reference derives deltatime from the rank's OWN volo(0) (lulesh-init.cc:192), which
+ * differs by an ulp between ranks for sizes whose coordinates are not exact in binary
+ * (SURVEY F10).  The product and ora_new() use the global-origin element on every rank; this
+ * switch restores the reference's per-rank value so that the multi-rank emulation can be
+ * pinned bit-for-bit against the reference's MPI build (oracle/_ref/lulesh_mpi). */
+void ora_use_reference_dt0(ora_domain *d)
+{
+   const int G = imax3(d->px * d->sx, d->py * d->sy, d->pz * d->sz);
+   const double scale = (double)G / 45.0;
+   const double einit = 3.948746e+7 * scale * scale * scale;
+   d->s.deltatime = (.5 * cbrt(F(d, VOLO)[0])) / sqrt(2.0 * einit);
+}
+
 void ora_free(ora_domain *d)
 {
    if (!d) return;

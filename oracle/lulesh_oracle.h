@@ -27,6 +27,7 @@ typedef struct ora_domain ora_domain;
 ora_domain *ora_new(int numRanks, int rank, int px, int py, int pz,
                     int sx, int sy, int sz, int numReg, int balance, int cost);
 void ora_free(ora_domain *d);
+void ora_use_reference_dt0(ora_domain *d);              /* lulesh-init.cc:192 as written (per-rank) */
 
 double *ora_real(ora_domain *d, int field);          /* field ids of lulesh_b200.h */
 size_t  ora_real_count(ora_domain *d, int field);

@@ -36,6 +36,7 @@ def load():
     lib.ora_new.restype = vp
     lib.ora_new.argtypes = [C.c_int] * 11
     lib.ora_free.argtypes = [vp]
+    lib.ora_use_reference_dt0.argtypes = [vp]
     lib.ora_real.restype = pd
     lib.ora_real.argtypes = [vp, C.c_int]
     lib.ora_real_count.restype = C.c_size_t
@@ -116,6 +117,9 @@ class OracleDomain:
     def time_constraints(self): self.lib.ora_time_constraints(self._p)
     def step(self): return self.lib.ora_step(self._p)
     def run(self, max_cycles=9999999): return self.lib.ora_run(self._p, max_cycles)
+
+    def use_reference_dt0(self):
+        self.lib.ora_use_reference_dt0(self._p)
 
     def symmetry(self, n=None):
         out = (C.c_double * 3)()

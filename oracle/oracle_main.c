@@ -26,7 +26,7 @@ static double ksum(const double *a, size_t n)
 
 int main(int argc, char **argv)
 {
-   int nx = 30, its = 9999999, nr = 11, balance = 1, cost = 1, px = 1, py = 1, pz = 1;
+   int nx = 30, its = 9999999, nr = 11, balance = 1, cost = 1, px = 1, py = 1, pz = 1, refdt0 = 0;
    for (int i = 1; i < argc; ++i) {
       if (!strcmp(argv[i], "-s") && i + 1 < argc) nx = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-i") && i + 1 < argc) its = atoi(argv[++i]);
@@ -34,11 +34,14 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-b") && i + 1 < argc) balance = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-c") && i + 1 < argc) cost = atoi(argv[++i]);
       else if (!strcmp(argv[i], "--decomp") && i + 1 < argc) sscanf(argv[++i], "%dx%dx%d", &px, &py, &pz);
+      else if (!strcmp(argv[i], "--reference-dt0")) refdt0 = 1;
       else if (!strcmp(argv[i], "-q")) {}
       else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 255; }
    }
    ora_multi *m = ora_multi_new(px, py, pz, nx, nx, nx, nr, balance, cost);
    if (!m) { fprintf(stderr, "bad configuration\n"); return 255; }
+   if (refdt0)
+      for (int r = 0; r < px * py * pz; ++r) ora_use_reference_dt0(ora_multi_rank(m, r));
    double t0 = now();
    int rc = ora_multi_run(m, its);
    double el = now() - t0;

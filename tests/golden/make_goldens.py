@@ -6,6 +6,9 @@ compiles from /root/reference):
 
     make -C oracle ref && python tests/golden/make_goldens.py [--long]
 
+The `lulesh_mpi -np N ...` records come from the reference's own MPI code paths
+(lulesh-comm.cc) compiled unmodified against oracle/mpishim (no MPI exists in this image).
+
 Outputs (committed):
   tests/golden/ref_goldens.json   REFJSON records (cycles, %.17g e0, checksums,
                                   symmetry triple, region sizes) per run
@@ -53,6 +56,21 @@ def run(binary, args, threads=4, dump=None):
     raise RuntimeError("no REFJSON line")
 
 
+def run_mpi(np_, args, threads=2):
+    """The reference's USE_MPI=1 build under the single-node MPI stand-in (oracle/mpishim).
+    OMP_NUM_THREADS >= 2 selects the reference's threaded force path (lulesh.cc:514), the
+    canonical summation order of this project."""
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    p = subprocess.run([os.path.join(REF, "mpirun_shim"), "-np", str(np_), os.path.join(REF, "lulesh_mpi")]
+                       + args.split(), env=env, capture_output=True, text=True, check=True)
+    for line in p.stdout.splitlines():
+        if line.startswith("REFJSON "):
+            rec = json.loads(line[len("REFJSON "):])
+            rec.pop("elapsed", None)
+            return rec
+    raise RuntimeError("no REFJSON line")
+
+
 def main():
     runs = [
         ("lulesh_omp", "-s 30 -i 100"),
@@ -74,6 +92,11 @@ def main():
     for binary, args in runs:
         key = f"{binary} {args}"
         gold[key] = run(binary, args)
+        print(key, gold[key]["cycles"], gold[key]["e0"])
+    for np_, args in ((8, "-s 5"), (8, "-s 6"), (8, "-s 8 -i 100"), (8, "-s 10 -i 60"), (8, "-s 12 -i 120"),
+                      (27, "-s 3 -i 60")):
+        key = f"lulesh_mpi -np {np_} {args}"
+        gold[key] = run_mpi(np_, args)
         print(key, gold[key]["cycles"], gold[key]["e0"])
     for tag in ("s90", "s128"):
         p = f"/tmp/gold/{tag}.out"

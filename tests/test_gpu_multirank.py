@@ -101,6 +101,23 @@ def test_eight_ranks_against_reference_golden(lb, goldens):
     assert abs(out[0]["e"][0] - gold["e0"]) <= 1e-8 * gold["e0"]
 
 
+def test_eight_ranks_against_reference_mpi_build(lb, goldens):
+    """Same layout, same per-rank region lists (srand(rank), rotation) as the reference's own
+    USE_MPI=1 run (`mpirun_shim -np 8 lulesh_mpi -s 12 -i 120`, tests/golden): rank 0's
+    cycle count, origin energy and checksums."""
+    if ngpu() < 8:
+        pytest.skip("needs 8 GPUs")
+    gold = goldens["lulesh_mpi -np 8 -s 12 -i 120"]
+    out = run_ranks(lb, (2, 2, 2), (12, 12, 12), 120)
+    r0 = out[0]
+    assert r0["s"].cycle == gold["cycles"]
+    assert abs(r0["s"].time - gold["time"]) <= 1e-12 * gold["time"]
+    assert abs(r0["e"][0] - gold["e0"]) <= 1e-9 * gold["e0"]
+    for name, key in (("e", "sum_e"), ("p", "sum_p"), ("q", "sum_q"), ("v", "sum_v")):
+        assert abs(float(np.sum(r0[name])) - gold[key]) <= 1e-9 * abs(gold[key]) + 1e-12, name
+    assert [len(r0["dom"].region_list(i)) for i in range(11)] == gold["regions"]
+
+
 def test_two_rank_driver_binary(lb, goldens):
     if ngpu() < 2:
         pytest.skip("needs 2 GPUs")

@@ -125,6 +125,34 @@ def test_multi_rank_emulation_matches_single_domain(oracle_mod):
         assert abs(r0.field("e")[0] - single.field("e")[0]) <= 1e-12 * single.field("e")[0]
 
 
+@pytest.mark.parametrize("key,decomp,n,its", [
+    ("lulesh_mpi -np 8 -s 5", (2, 2, 2), 5, 9999999), ("lulesh_mpi -np 8 -s 6", (2, 2, 2), 6, 9999999),
+    ("lulesh_mpi -np 8 -s 8 -i 100", (2, 2, 2), 8, 100), ("lulesh_mpi -np 8 -s 10 -i 60", (2, 2, 2), 10, 60),
+    ("lulesh_mpi -np 27 -s 3 -i 60", (3, 3, 3), 3, 60)])
+def test_multi_rank_emulation_bit_identical_to_reference_mpi_build(oracle_mod, goldens, key, decomp, n, its):
+    """The reference's USE_MPI=1 build (its own CommSBN / CommSyncPosVel / CommMonoQ and
+    MPI_Allreduce code, compiled unmodified against oracle/mpishim) versus the oracle's
+    in-process emulation of a rank grid: rank 0's scalars and checksums, bit for bit.
+    The reference derives dt0 per rank (lulesh-init.cc:192), hence use_reference_dt0()."""
+    gold = goldens[key]
+    m = oracle_mod.OracleMulti(decomp, (n, n, n))
+    for r in range(m.n):
+        m.rank(r).use_reference_dt0()
+    assert m.run(its) == 0
+    d = m.rank(0)
+    s, f = d.scalars, d.field
+    sym = d.symmetry(n)
+    got = {"cycles": s.cycle, "e0": f("e")[0], "time": s.time, "dt": s.deltatime,
+           "dtcourant": s.dtcourant, "dthydro": s.dthydro, "sum_e": _seqsum(f("e")),
+           "sum_p": _seqsum(f("p")), "sum_q": _seqsum(f("q")), "sum_v": _seqsum(f("v")),
+           "sum_ss": _seqsum(f("ss")), "sum_xyz": _seqsum(f("x") + f("y") + f("z")),
+           "sum_absvel": _seqsum(np.abs(f("xd")) + np.abs(f("yd")) + np.abs(f("zd"))),
+           "max_abs_diff": sym[0], "total_abs_diff": sym[1], "max_rel_diff": sym[2]}
+    for k in CHECK_KEYS:
+        assert got[k] == gold[k], f"{key}: {k} emulation {got[k]!r} != reference MPI {gold[k]!r}"
+    assert [len(d.region_list(i)) for i in range(11)] == gold["regions"]
+
+
 def test_oracle_error_codes(oracle_mod):
     d = oracle_mod.OracleDomain(4)
     d.field("v")[3] = -1.0
