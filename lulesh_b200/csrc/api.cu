@@ -406,7 +406,7 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    for (int i = 0; i < v->numSymmY; ++i) nodeFlags[v->symmY[i]] |= NODE_SYMM_Y;
    for (int i = 0; i < v->numSymmZ; ++i) nodeFlags[v->symmZ[i]] |= NODE_SYMM_Z;
 
-   // ---- region work list.  Every region is padded to whole blocks so that the EOS
+   // ---- region work list.  Every cost class is padded to whole blocks so that the EOS
    // repetition count is block-uniform (no divergence in the rep loop).  Block order:
    // the blocks of the most expensive repetition class are FP64-bound, the cheap ones are
    // bound by their three dependent gathers; interleaving them lets each SM overlap the
@@ -422,24 +422,33 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
          const int rep = region_rep(r, v->numReg, v->cost);
          if (v->regElemSize[r] > 0) { max_rep = std::max(max_rep, rep); min_rep = std::min(min_rep, rep); }
       }
-      std::vector<int> order(v->numReg);
-      for (int r = 0; r < v->numReg; ++r) order[r] = r;
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-         return region_rep(a, v->numReg, v->cost) > region_rep(b, v->numReg, v->cost);
-      });
-      for (int r : order) {
-         const int n = v->regElemSize[r], rep = region_rep(r, v->numReg, v->cost);
-         total += n;
+      // Regions with the same repetition count are one cost class: every element is the same
+      // material, only `rep` differs (lulesh.cc:2393-2400).  The lists of a class are merged
+      // and sorted by element id, which lengthens the contiguous runs a warp sees (the
+      // per-region lists are fragmented into runs of ~38 elements by CreateRegionIndexSets).
+      std::vector<int> classes;
+      for (int r = 0; r < v->numReg; ++r) {
+         const int rep = region_rep(r, v->numReg, v->cost);
+         if (std::find(classes.begin(), classes.end(), rep) == classes.end()) classes.push_back(rep);
+      }
+      std::sort(classes.begin(), classes.end(), std::greater<int>());
+      for (int rep : classes) {
+         std::vector<int> merged;
+         for (int r = 0; r < v->numReg; ++r) {
+            if (region_rep(r, v->numReg, v->cost) != rep) continue;
+            const int n = v->regElemSize[r];
+            total += n;
+            for (int t = 0; t < n; ++t) {
+               const int el = v->regElemlist[r][t];
+               if (el < 0 || el >= ne) return fail(LULESH_B200_EINVAL, "region list entry out of range");
+               merged.push_back(el);
+            }
+         }
+         std::sort(merged.begin(), merged.end());
+         const int n = (int)merged.size();
          for (int t0 = 0; t0 < n; t0 += MAT_THREADS) {
             Block b{(int)entries.size(), rep};
-            for (int t = t0; t < t0 + MAT_THREADS; ++t) {
-               int el = -1;
-               if (t < n) {
-                  el = v->regElemlist[r][t];
-                  if (el < 0 || el >= ne) return fail(LULESH_B200_EINVAL, "region list entry out of range");
-               }
-               entries.push_back(el);
-            }
+            for (int t = t0; t < t0 + MAT_THREADS; ++t) entries.push_back(t < n ? merged[t] : -1);
             ((rep == max_rep && max_rep > min_rep) ? heavy : light).push_back(b);
          }
       }
