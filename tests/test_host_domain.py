@@ -131,3 +131,30 @@ def test_cli_help_and_errors(lb):
     assert "Parse Error on option -i integer value required after argument" in p.stdout
     p = _cli(lb, "-v")
     assert p.returncode == 255 and "Use of -v requires compiling with -DVIZ_MESH" in p.stdout
+
+
+def test_create_rejects_bad_views_before_touching_the_gpu(lb):
+    """Argument validation happens before any CUDA call, so it is testable here."""
+    import ctypes as C
+    h = C.c_void_p()
+    d = lb.Domain(4)
+    assert lb._lib.lulesh_b200_create(None, 0, None, C.byref(h)) == lb.EINVAL
+    v = lb.HostView.from_buffer_copy(d.refresh_view())
+    v.abi_version = 99
+    assert lb._lib.lulesh_b200_create(C.byref(v), 0, None, C.byref(h)) == lb.EINVAL
+    assert b"abi_version" in lb._lib.lulesh_b200_last_error()
+    v = lb.HostView.from_buffer_copy(d.refresh_view())
+    v.numNode += 1
+    assert lb._lib.lulesh_b200_create(C.byref(v), 0, None, C.byref(h)) == lb.EINVAL
+    v = lb.HostView.from_buffer_copy(d.refresh_view())
+    v.numRanks = 3
+    assert lb._lib.lulesh_b200_create(C.byref(v), 0, None, C.byref(h)) == lb.EINVAL
+    v = lb.HostView.from_buffer_copy(d.refresh_view())
+    v.nodelist = None
+    assert lb._lib.lulesh_b200_create(C.byref(v), 0, None, C.byref(h)) == lb.EINVAL
+    assert not h.value
+    # null handles are rejected, not dereferenced
+    assert lb._lib.lulesh_b200_step(None) == lb.EINVAL
+    assert lb._lib.lulesh_b200_run(None, 1, 1, lb.PROGRESS_CB(), None) == lb.EINVAL
+    assert lb._lib.lulesh_b200_field_count(None, 0) == 0
+    lb._lib.lulesh_b200_destroy(None)
