@@ -18,7 +18,11 @@ $(OBJ)/kernels.o: $(CSRC)/kernels.cu $(CSRC)/kernels.cuh include/lulesh_b200.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJ)/kernels.ptxas.log || (cat $(OBJ)/kernels.ptxas.log; false)
 
-$(OBJ)/api.o: $(CSRC)/api.cu $(CSRC)/kernels.cuh include/lulesh_b200.h
+$(OBJ)/api.o: $(CSRC)/api.cu $(CSRC)/kernels.cuh $(CSRC)/setup.cuh $(CSRC)/host/domain.h include/lulesh_b200.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(OBJ)/setup.o: $(CSRC)/setup.cu $(CSRC)/setup.cuh $(CSRC)/kernels.cuh include/lulesh_b200.h
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
@@ -26,7 +30,7 @@ $(OBJ)/%.o: $(CSRC)/host/%.cc $(CSRC)/host/domain.h include/lulesh_b200.h includ
 	@mkdir -p $(OBJ)
 	$(HOSTCXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(OBJ)/kernels.o $(OBJ)/api.o $(OBJ)/domain.o $(OBJ)/host_capi.o $(OBJ)/driver.o
+$(LIB): $(OBJ)/kernels.o $(OBJ)/api.o $(OBJ)/setup.o $(OBJ)/domain.o $(OBJ)/host_capi.o $(OBJ)/driver.o
 	@mkdir -p lulesh_b200/lib
 	$(NVCC) $(ARCH) -shared -cudart static -ccbin $(HOSTCXX) -o $@ $^ -ldl -lpthread
 

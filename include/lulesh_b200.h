@@ -149,6 +149,22 @@ int lulesh_b200_get_unique_id(void *out_id /* 128 bytes */);
 int lulesh_b200_create(const lulesh_b200_host_view *view, int device,
                        const void *unique_id, lulesh_b200 **out);
 
+/* Device-side alternative to building a host Domain first: replaces
+ * Domain::Domain (lulesh-init.cc:16-194) for the Sedov problem.  BuildMesh (218-267), the
+ * node->corner lists (272-337), symmetry planes, connectivity and boundary conditions
+ * (514-673), volo / elemMass / nodalMass (159-178), the energy deposit and dt0 (183-192) are
+ * generated by setup kernels directly in HBM, bit-identical to the host Domain; only the
+ * region index sets (sequential glibc rand(), 401-510) are built on the host. */
+typedef struct lulesh_b200_sedov_params {
+   int32_t abi_version;                 /* LULESH_B200_ABI_VERSION */
+   int32_t numRanks, rank;
+   int32_t px, py, pz;                  /* ranks per axis; the reference: px = py = pz = tp */
+   int32_t sx, sy, sz;                  /* elements per edge of this rank's brick; the reference: nx */
+   int32_t numReg, balance, cost;       /* -r -b -c */
+} lulesh_b200_sedov_params;
+int lulesh_b200_create_sedov(const lulesh_b200_sedov_params *params, int device,
+                             const void *unique_id, lulesh_b200 **out);
+
 /* Replaces the initial nodalMass halo sum (lulesh.cc:2720-2729) and the
  * MPI_Barrier that follows (lulesh.cc:2732).  No-op at numRanks == 1. */
 int lulesh_b200_sum_nodal_mass(lulesh_b200 *h);

@@ -75,11 +75,15 @@ class HostView(C.Structure):
            ("constants", Constants), ("scalars", Scalars)])
 
 
+class SedovParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in "abi_version numRanks rank px py pz sx sy sz numReg balance cost".split()]
+
+
 PROGRESS_CB = C.CFUNCTYPE(None, C.c_int32, C.c_double, C.c_double, C.c_void_p)
 
 # every symbol declared in include/lulesh_b200.h and include/lulesh_host.h
 ABI_SYMBOLS = (
-    "lulesh_b200_get_unique_id lulesh_b200_create lulesh_b200_sum_nodal_mass lulesh_b200_run "
+    "lulesh_b200_get_unique_id lulesh_b200_create lulesh_b200_create_sedov lulesh_b200_sum_nodal_mass lulesh_b200_run "
     "lulesh_b200_step lulesh_b200_get_scalars lulesh_b200_set_scalars lulesh_b200_download "
     "lulesh_b200_upload lulesh_b200_field_count lulesh_b200_set_debug "
     "lulesh_b200_kernel_time_increment lulesh_b200_kernel_force lulesh_b200_kernel_node "
@@ -102,6 +106,7 @@ def _sig(name, restype, *argtypes):
 _vp = C.c_void_p
 _sig("lulesh_b200_get_unique_id", C.c_int, _vp)
 _sig("lulesh_b200_create", C.c_int, C.POINTER(HostView), C.c_int, _vp, C.POINTER(_vp))
+_sig("lulesh_b200_create_sedov", C.c_int, C.POINTER(SedovParams), C.c_int, _vp, C.POINTER(_vp))
 _sig("lulesh_b200_sum_nodal_mass", C.c_int, _vp)
 _sig("lulesh_b200_run", C.c_int, _vp, C.c_int32, C.c_int32, PROGRESS_CB, _vp)
 _sig("lulesh_b200_step", C.c_int, _vp)
@@ -243,6 +248,22 @@ class Device:
         if rc:
             self._h = None
             raise LuleshError(rc, "lulesh_b200_create")
+
+    @classmethod
+    def sedov(cls, nx=30, num_reg=11, balance=1, cost=1, *, num_ranks=1, rank=0, decomp=None, sizes=None,
+              device=0, unique_id: bytes | None = None):
+        """Device-side setup (lulesh_b200_create_sedov): no host Domain is built."""
+        px, py, pz = decomp if decomp else decompose(num_ranks)
+        sx, sy, sz = sizes if sizes else (nx, nx, nx)
+        p = SedovParams(ABI_VERSION, num_ranks, rank, px, py, pz, sx, sy, sz, num_reg, balance, cost)
+        self = cls.__new__(cls)
+        self._h, self.domain = _vp(), None
+        uid = C.create_string_buffer(unique_id, UNIQUE_ID_BYTES) if unique_id else None
+        rc = _lib.lulesh_b200_create_sedov(C.byref(p), device, uid, C.byref(self._h))
+        if rc:
+            self._h = None
+            raise LuleshError(rc, "lulesh_b200_create_sedov")
+        return self
 
     def _check(self, rc, what):
         if rc:

@@ -21,6 +21,8 @@
 
 #include "../../include/lulesh_b200.h"
 #include "kernels.cuh"
+#include "setup.cuh"
+#include "host/domain.h"
 
 using namespace lb200;
 
@@ -268,8 +270,11 @@ extern "C" int lulesh_b200_get_unique_id(void *out_id)
 static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void *unique_id,
                       std::vector<unsigned char> &nodeFlags);
 
+// `gen` != NULL: device-side Sedov setup (lulesh_b200_create_sedov): the view carries sizes,
+// decomposition, constants, scalars and the region lists only; every other array is generated
+// in HBM by the kernels of setup.cu.
 static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int device,
-                       const void *unique_id)
+                       const void *unique_id, const SetupParams *gen)
 {
    if (v->abi_version != LULESH_B200_ABI_VERSION)
       return fail(LULESH_B200_EINVAL, "abi_version %d != %d", v->abi_version, LULESH_B200_ABI_VERSION);
@@ -279,8 +284,11 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
       return fail(LULESH_B200_EINVAL, "inconsistent sizes in host view");
    if (v->numRanks < 1 || v->px * v->py * v->pz != v->numRanks || v->rank < 0 || v->rank >= v->numRanks)
       return fail(LULESH_B200_EINVAL, "inconsistent decomposition in host view");
-   if (!v->x || !v->nodelist || !v->nodeElemStart || !v->nodeElemCornerList || !v->regElemSize ||
-       !v->regElemlist || v->numReg < 1)
+   if (!v->regElemSize || !v->regElemlist || v->numReg < 1 ||
+       (!gen && (!v->x || !v->y || !v->z || !v->xd || !v->yd || !v->zd || !v->nodalMass || !v->nodelist ||
+                 !v->lxim || !v->lxip || !v->letam || !v->letap || !v->lzetam || !v->lzetap || !v->elemBC ||
+                 !v->e || !v->p || !v->q || !v->v || !v->volo || !v->ss || !v->elemMass ||
+                 !v->nodeElemStart || !v->nodeElemCornerList)))
       return fail(LULESH_B200_EINVAL, "null array in host view");
 
    int ndev = 0;
@@ -328,7 +336,7 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
 
    // ---- node-centred state
 #define UP_NODE(name, id)                                                               \
-   { double *p_; if ((rc = dev_upload(h, &p_, v->name, (size_t)nn))) return rc;         \
+   { double *p_; if ((rc = gen ? dev_zero(h, &p_, (size_t)nn) : dev_upload(h, &p_, v->name, (size_t)nn))) return rc; \
      h->field_ptr[id] = p_; h->field_cnt[id] = nn; }
    UP_NODE(x, LULESH_F_X) UP_NODE(y, LULESH_F_Y) UP_NODE(z, LULESH_F_Z)
    UP_NODE(xd, LULESH_F_XD) UP_NODE(yd, LULESH_F_YD) UP_NODE(zd, LULESH_F_ZD)
@@ -346,13 +354,13 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
 
    // ---- element-centred state
 #define UP_ELEM(name, id, dst)                                                          \
-   { double *p_; if ((rc = dev_upload(h, &p_, v->name, (size_t)ne))) return rc;         \
+   { double *p_; if ((rc = gen ? dev_zero(h, &p_, (size_t)ne) : dev_upload(h, &p_, v->name, (size_t)ne))) return rc; \
      h->field_ptr[id] = p_; h->field_cnt[id] = ne; dst = p_; }
    UP_ELEM(e, LULESH_F_E, P.e) UP_ELEM(p, LULESH_F_P, P.p) UP_ELEM(q, LULESH_F_Q, P.q)
    UP_ELEM(v, LULESH_F_V, P.v) UP_ELEM(ss, LULESH_F_SS, P.ss)
-   { double *p_; if ((rc = dev_upload(h, &p_, v->volo, (size_t)ne))) return rc;
+   { double *p_; if ((rc = gen ? dev_zero(h, &p_, (size_t)ne) : dev_upload(h, &p_, v->volo, (size_t)ne))) return rc;
      h->field_ptr[LULESH_F_VOLO] = p_; h->field_cnt[LULESH_F_VOLO] = ne; P.volo = p_; }
-   { double *p_; if ((rc = dev_upload(h, &p_, v->elemMass, (size_t)ne))) return rc;
+   { double *p_; if ((rc = gen ? dev_zero(h, &p_, (size_t)ne) : dev_upload(h, &p_, v->elemMass, (size_t)ne))) return rc;
      h->field_ptr[LULESH_F_ELEMMASS] = p_; h->field_cnt[LULESH_F_ELEMMASS] = ne; P.elemMass = p_; }
 #undef UP_ELEM
 #define ZERO_ELEM(id, dst, cnt)                                                         \
@@ -374,7 +382,7 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    for (int a = 0; a < 3; ++a) h->field_cnt[LULESH_F_DELV_XI + a] = P.allElem;
    {
       int *p_;
-#define UP_INT(name, cnt) if ((rc = dev_upload(h, &p_, v->name, (size_t)(cnt)))) return rc; P.name = p_;
+#define UP_INT(name, cnt) if ((rc = gen ? dev_zero(h, &p_, (size_t)(cnt)) : dev_upload(h, &p_, v->name, (size_t)(cnt)))) return rc; P.name = p_;
       UP_INT(nodelist, 8 * (size_t)ne)
       UP_INT(lxim, ne) UP_INT(lxip, ne) UP_INT(letam, ne) UP_INT(letap, ne)
       UP_INT(lzetam, ne) UP_INT(lzetap, ne) UP_INT(elemBC, ne)
@@ -382,6 +390,26 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    }
    if ((rc = dev_zero(h, &P.fcorner, (size_t)24 * P.ne_pad))) return rc;
 
+   std::vector<unsigned char> nodeFlags(nn, 0);
+   unsigned char *d_nodeFlags = nullptr;
+   if (gen) {
+      // ---- device-side setup: mesh, corner table, connectivity, BCs, flags, volumes, masses
+      int *d_ell = nullptr;
+      if ((rc = dev_alloc(h, &d_ell, (size_t)8 * P.nn_pad))) return rc;
+      if ((rc = dev_alloc(h, &d_nodeFlags, (size_t)nn))) return rc;
+      k_setup_nodes<<<blocks_for(nn, 256), 256, 0, h->stream>>>(*gen, P.x, P.y, P.z, d_nodeFlags, d_ell, nn,
+                                                                P.nn_pad, P.ne_pad);
+      k_setup_elems<<<blocks_for(ne, 256), 256, 0, h->stream>>>(
+         *gen, P.x, P.y, P.z, const_cast<int *>(P.nodelist), const_cast<int *>(P.lxim),
+         const_cast<int *>(P.lxip), const_cast<int *>(P.letam), const_cast<int *>(P.letap),
+         const_cast<int *>(P.lzetam), const_cast<int *>(P.lzetap), const_cast<int *>(P.elemBC),
+         const_cast<double *>(P.volo), const_cast<double *>(P.elemMass), P.v, P.e, ne);
+      k_setup_nodal_mass<<<blocks_for(nn, 256), 256, 0, h->stream>>>(
+         d_ell, P.volo, const_cast<double *>(P.nodalMass), nn, P.nn_pad, P.ne_pad);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(h->stream));
+      P.cornerEll = d_ell;
+   } else {
    // ---- corner gather table: CSR (lulesh-init.cc:295-319) -> 8-slot ELL, slot
    // order == CSR order == ascending element; entries re-based to the SoA planes
    {
@@ -401,10 +429,10 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    }
 
    // ---- per-node flags from the symmetry node sets (lulesh-init.cc:514-533)
-   std::vector<unsigned char> nodeFlags(nn, 0);
    for (int i = 0; i < v->numSymmX; ++i) nodeFlags[v->symmX[i]] |= NODE_SYMM_X;
    for (int i = 0; i < v->numSymmY; ++i) nodeFlags[v->symmY[i]] |= NODE_SYMM_Y;
    for (int i = 0; i < v->numSymmZ; ++i) nodeFlags[v->symmZ[i]] |= NODE_SYMM_Z;
+   }
 
    // ---- region work list.  Every cost class is padded to whole blocks so that the EOS
    // repetition count is block-uniform (no divergence in the rep loop).  Block order:
@@ -479,7 +507,9 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
       if ((rc = build_comm(h, v, unique_id, nodeFlags))) return rc;
    }
    for (int a = 0; a < 3; ++a) h->field_ptr[LULESH_F_DELV_XI + a] = P.delv_xi + (size_t)a * P.allElem;
-   {
+   if (gen) {
+      P.nodeFlags = d_nodeFlags;   // generated on the device, COMM bit included
+   } else {
       unsigned char *p_;
       if ((rc = dev_upload(h, &p_, nodeFlags.data(), nodeFlags.size()))) return rc;
       P.nodeFlags = p_;
@@ -819,7 +849,52 @@ extern "C" int lulesh_b200_create(const lulesh_b200_host_view *view, int device,
    if (!view || !out) return fail(LULESH_B200_EINVAL, "null argument");
    *out = nullptr;
    lulesh_b200 *h = new lulesh_b200();
-   const int rc = create_impl(h, view, device, unique_id);
+   const int rc = create_impl(h, view, device, unique_id, nullptr);
+   if (rc) { lulesh_b200_destroy(h); return rc; }
+   *out = h;
+   return 0;
+}
+
+extern "C" int lulesh_b200_create_sedov(const lulesh_b200_sedov_params *p, int device,
+                                        const void *unique_id, lulesh_b200 **out)
+{
+   if (!p || !out) return fail(LULESH_B200_EINVAL, "null argument");
+   *out = nullptr;
+   if (p->abi_version != LULESH_B200_ABI_VERSION) return fail(LULESH_B200_EINVAL, "abi_version mismatch");
+   if (p->px < 1 || p->py < 1 || p->pz < 1 || p->numRanks != p->px * p->py * p->pz || p->rank < 0 ||
+       p->rank >= p->numRanks || p->sx < 1 || p->sy < 1 || p->sz < 1 || p->numReg < 1)
+      return fail(LULESH_B200_EINVAL, "inconsistent Sedov parameters");
+   const long long ne = (long long)p->sx * p->sy * p->sz;
+   if (8 * ne > INT_MAX) return fail(LULESH_B200_EINVAL, "brick too large for int32 indices");
+
+   lulesh_b200_host_view v;
+   memset(&v, 0, sizeof v);
+   v.abi_version = LULESH_B200_ABI_VERSION;
+   v.sizeX = p->sx; v.sizeY = p->sy; v.sizeZ = p->sz;
+   v.numElem = (int)ne;
+   v.numNode = (p->sx + 1) * (p->sy + 1) * (p->sz + 1);
+   v.numRanks = p->numRanks; v.rank = p->rank;
+   v.px = p->px; v.py = p->py; v.pz = p->pz;
+   v.colLoc = p->rank % p->px; v.rowLoc = (p->rank / p->px) % p->py; v.planeLoc = p->rank / (p->px * p->py);
+   v.numReg = p->numReg; v.cost = p->cost;
+
+   SetupParams S;
+   S.sx = p->sx; S.sy = p->sy; S.sz = p->sz; S.px = p->px; S.py = p->py; S.pz = p->pz;
+   S.col = v.colLoc; S.row = v.rowLoc; S.plane = v.planeLoc; S.numRanks = p->numRanks;
+   S.G = std::max(p->px * p->sx, std::max(p->py * p->sy, p->pz * p->sz));
+   SedovInitialScalars(S.G, &v.scalars, &v.constants, &S.einit);
+
+   // region index sets: sequential glibc rand(), host only (lulesh-init.cc:401-510)
+   std::vector<Index_t> regNumList, regElemSize;
+   std::vector<std::vector<Index_t>> lists;
+   CreateRegionIndexSetsHost(p->rank, v.numElem, p->numReg, p->balance, regNumList, regElemSize, lists);
+   std::vector<const int32_t *> ptrs(p->numReg);
+   for (int r = 0; r < p->numReg; ++r) ptrs[r] = lists[r].data();
+   v.regElemSize = regElemSize.data();
+   v.regElemlist = ptrs.data();
+
+   lulesh_b200 *h = new lulesh_b200();
+   const int rc = create_impl(h, &v, device, unique_id, &S);
    if (rc) { lulesh_b200_destroy(h); return rc; }
    *out = h;
    return 0;

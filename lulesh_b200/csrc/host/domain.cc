@@ -72,12 +72,8 @@ void Domain::Init(Int_t nr, Int_t balance)
    m_numElem = (Index_t)ne;
    m_numNode = (Index_t)nn;
 
-   // constants, lulesh-init.cc:20-38
-   m_c.e_cut = 1.0e-7; m_c.p_cut = 1.0e-7; m_c.q_cut = 1.0e-7; m_c.v_cut = 1.0e-10; m_c.u_cut = 1.0e-7;
-   m_c.hgcoef = 3.0; m_c.ss4o3 = 4.0 / 3.0; m_c.qstop = 1.0e+12; m_c.monoq_max_slope = 1.0;
-   m_c.monoq_limiter_mult = 2.0; m_c.qlc_monoq = 0.5; m_c.qqc_monoq = 2.0 / 3.0; m_c.qqc = 2.0;
-   m_c.eosvmax = 1.0e+9; m_c.eosvmin = 1.0e-9; m_c.pmin = 0.; m_c.emin = -1.0e+15;
-   m_c.dvovmax = 0.1; m_c.refdens = 1.0;
+   Real_t einit_unused;
+   SedovInitialScalars(longestEdge(m_px * m_sizeX, m_py * m_sizeY, m_pz * m_sizeZ), &m_s, &m_c, &einit_unused);
 
    // AllocateElemPersistent / AllocateNodePersistent + basic field init
    // (lulesh.h:164-219, lulesh-init.cc:90-116): e = p = q = ss = 0, v = 1, velocities 0
@@ -92,12 +88,6 @@ void Domain::Init(Int_t nr, Int_t balance)
    CreateRegionIndexSets(nr, balance);
    SetupSymmetryPlanes();
    SetupElementConnectivitiesAndBCs();
-
-   // time controls, lulesh-init.cc:146-156
-   m_s.dtfixed = -1.0e-6; m_s.stoptime = 1.0e-2;
-   m_s.deltatimemultlb = 1.1; m_s.deltatimemultub = 1.2;
-   m_s.dtcourant = 1.0e+20; m_s.dthydro = 1.0e+20; m_s.dtmax = 1.0e-2;
-   m_s.time = 0.; m_s.cycle = 0; m_s.error = 0; m_s.deltatime = 0.;
 
    InitializeFieldData();
 }
@@ -147,15 +137,16 @@ void Domain::SetupThreadSupportStructures()
 
 // lulesh-init.cc:401-510: weighted random runs of elements per region, drawn
 // from glibc rand() seeded with the rank; region ids rotate with the rank.
-void Domain::CreateRegionIndexSets(Int_t nr, Int_t balance)
+void CreateRegionIndexSetsHost(Int_t rank, Index_t numElem, Int_t nr, Int_t balance,
+                               std::vector<Index_t> &regNumList, std::vector<Index_t> &regElemSize,
+                               std::vector<std::vector<Index_t>> &regElemlist)
 {
-   srand(m_rank);
-   m_numReg = nr;
-   m_regElemSize.assign(nr, 0);
-   m_regNumList.assign(m_numElem, 0);
+   srand(rank);
+   regElemSize.assign(nr, 0);
+   regNumList.assign(numElem, 0);
    Index_t next = 0;
    if (nr == 1) {
-      std::fill(m_regNumList.begin(), m_regNumList.end(), 1);
+      std::fill(regNumList.begin(), regNumList.end(), 1);
    } else {
       std::vector<Int_t> binEnd(nr);
       Int_t costDenominator = 0, lastReg = -1;
@@ -167,9 +158,9 @@ void Domain::CreateRegionIndexSets(Int_t nr, Int_t balance)
          const Int_t var = rand() % costDenominator;
          Int_t i = 0;
          while (var >= binEnd[i]) ++i;
-         return ((i + m_rank) % nr) + 1;
+         return ((i + rank) % nr) + 1;
       };
-      while (next < m_numElem) {
+      while (next < numElem) {
          Int_t regionNum = draw();
          while (regionNum == lastReg) regionNum = draw();
          const Int_t bin = rand() % 1000;
@@ -181,17 +172,50 @@ void Domain::CreateRegionIndexSets(Int_t nr, Int_t balance)
          else if (bin < 978) run = rand() % 128 + 128;
          else if (bin < 981) run = rand() % 256 + 256;
          else run = rand() % 1537 + 512;
-         const Index_t stop = std::min<long long>((long long)next + run, m_numElem);
-         while (next < stop) m_regNumList[next++] = regionNum;
+         const Index_t stop = std::min<long long>((long long)next + run, numElem);
+         while (next < stop) regNumList[next++] = regionNum;
          lastReg = regionNum;
       }
    }
-   for (Index_t i = 0; i < m_numElem; ++i) ++m_regElemSize[m_regNumList[i] - 1];
-   m_regElemlist.assign(nr, {});
-   for (Int_t r = 0; r < nr; ++r) m_regElemlist[r].reserve(m_regElemSize[r]);
-   for (Index_t i = 0; i < m_numElem; ++i) m_regElemlist[m_regNumList[i] - 1].push_back(i);
+   for (Index_t i = 0; i < numElem; ++i) ++regElemSize[regNumList[i] - 1];
+   regElemlist.assign(nr, {});
+   for (Int_t r = 0; r < nr; ++r) regElemlist[r].reserve(regElemSize[r]);
+   for (Index_t i = 0; i < numElem; ++i) regElemlist[regNumList[i] - 1].push_back(i);
+}
+
+void Domain::CreateRegionIndexSets(Int_t nr, Int_t balance)
+{
+   m_numReg = nr;
+   CreateRegionIndexSetsHost(m_rank, m_numElem, nr, balance, m_regNumList, m_regElemSize, m_regElemlist);
    m_regElemlistPtrs.resize(nr);
    for (Int_t r = 0; r < nr; ++r) m_regElemlistPtrs[r] = m_regElemlist[r].data();
+}
+
+// constants (lulesh-init.cc:20-38), time controls (146-156), deposited energy (183-185) and
+// the initial time step (192) from the volume of the GLOBAL origin element
+void SedovInitialScalars(Index_t G, lulesh_b200_scalars *s, lulesh_b200_constants *c, Real_t *einit)
+{
+   c->e_cut = 1.0e-7; c->p_cut = 1.0e-7; c->q_cut = 1.0e-7; c->v_cut = 1.0e-10; c->u_cut = 1.0e-7;
+   c->hgcoef = 3.0; c->ss4o3 = 4.0 / 3.0; c->qstop = 1.0e+12; c->monoq_max_slope = 1.0;
+   c->monoq_limiter_mult = 2.0; c->qlc_monoq = 0.5; c->qqc_monoq = 2.0 / 3.0; c->qqc = 2.0;
+   c->eosvmax = 1.0e+9; c->eosvmin = 1.0e-9; c->pmin = 0.; c->emin = -1.0e+15;
+   c->dvovmax = 0.1; c->refdens = 1.0;
+   s->dtfixed = -1.0e-6; s->stoptime = 1.0e-2;
+   s->deltatimemultlb = 1.1; s->deltatimemultub = 1.2;
+   s->dtcourant = 1.0e+20; s->dthydro = 1.0e+20; s->dtmax = 1.0e-2;
+   s->time = 0.; s->cycle = 0; s->error = 0;
+   const Real_t scale = Real_t(G) / Real_t(45.0);
+   *einit = Real_t(3.948746e+7) * scale * scale * scale;
+   Real_t xo[8], yo[8], zo[8];
+   for (int k = 0; k < 8; ++k) {
+      const int i = (k == 1 || k == 2 || k == 5 || k == 6);
+      const int j = (k == 2 || k == 3 || k == 6 || k == 7);
+      const int l = (k >= 4);
+      xo[k] = Real_t(1.125) * Real_t(i) / Real_t(G);
+      yo[k] = Real_t(1.125) * Real_t(j) / Real_t(G);
+      zo[k] = Real_t(1.125) * Real_t(l) / Real_t(G);
+   }
+   s->deltatime = (Real_t(.5) * cbrt(CalcElemVolume(xo, yo, zo))) / sqrt(Real_t(2.0) * (*einit));
 }
 
 // lulesh-init.cc:514-533; a set exists only on ranks touching the global min plane
@@ -283,26 +307,15 @@ void Domain::InitializeFieldData()
       m_elemMass[i] = volume;
       for (int c = 0; c < 8; ++c) m_nodalMass[nl[c]] += volume / Real_t(8.0);
    }
-   const Index_t G = longestEdge(m_px * m_sizeX, m_py * m_sizeY, m_pz * m_sizeZ);
-   const Real_t ebase = Real_t(3.948746e+7);
-   const Real_t scale = Real_t(G) / Real_t(45.0);
-   const Real_t einit = ebase * scale * scale * scale;
+   // energy deposit (lulesh-init.cc:183-190); deltatime was set by SedovInitialScalars from the
+   // GLOBAL origin element: the reference's per-rank volo(0) (lulesh-init.cc:192) is not
+   // bit-identical across ranks for sizes such as 640, and on the origin rank the
+   // two coincide.
+   lulesh_b200_scalars s_unused;
+   lulesh_b200_constants c_unused;
+   Real_t einit;
+   SedovInitialScalars(longestEdge(m_px * m_sizeX, m_py * m_sizeY, m_pz * m_sizeZ), &s_unused, &c_unused, &einit);
    if (m_rowLoc + m_colLoc + m_planeLoc == 0) m_e[0] = einit;
-
-   // The reference derives dt0 from the rank's own volo(0) (lulesh-init.cc:192),
-   // which is not bit-identical across ranks for sizes such as 640.
-   // Every rank uses the volume of the GLOBAL origin element instead; on the
-   // origin rank that is volo(0), i.e. exactly the reference's value.
-   Real_t xo[8], yo[8], zo[8];
-   for (int c = 0; c < 8; ++c) {
-      const int i = (c == 1 || c == 2 || c == 5 || c == 6);
-      const int j = (c == 2 || c == 3 || c == 6 || c == 7);
-      const int k = (c >= 4);
-      xo[c] = Real_t(1.125) * Real_t(i) / Real_t(G);
-      yo[c] = Real_t(1.125) * Real_t(j) / Real_t(G);
-      zo[c] = Real_t(1.125) * Real_t(k) / Real_t(G);
-   }
-   m_s.deltatime = (Real_t(.5) * cbrt(CalcElemVolume(xo, yo, zo))) / sqrt(Real_t(2.0) * einit);
 }
 
 lulesh_b200_host_view Domain::view()

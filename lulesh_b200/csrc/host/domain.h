@@ -141,6 +141,15 @@ class Domain {
    Index_t m_sizeX, m_sizeY, m_sizeZ, m_numElem, m_numNode;
 };
 
+// Pieces of the setup that stay on the host even with device-side mesh generation
+// (lulesh_b200_create_sedov): the region index sets need glibc's sequential rand()
+// (lulesh-init.cc:401-510); the initial time controls and energy are a handful of scalars.
+void CreateRegionIndexSetsHost(Int_t rank, Index_t numElem, Int_t nr, Int_t balance,
+                               std::vector<Index_t> &regNumList, std::vector<Index_t> &regElemSize,
+                               std::vector<std::vector<Index_t>> &regElemlist);
+void SedovInitialScalars(Index_t globalEdge, lulesh_b200_scalars *s, lulesh_b200_constants *c,
+                         Real_t *einit);
+
 // CalcElemVolume (lulesh.cc:1274-1366), needed by the setup for volo/elemMass.
 Real_t CalcElemVolume(const Real_t x[8], const Real_t y[8], const Real_t z[8]);
 
@@ -150,4 +159,5 @@ struct cmdLineOpts {   // lulesh.h:599-609 plus the additive multi-GPU flags
    Int_t px, py, pz;      // --decomp PXxPYxPZ (default from lulesh_host_decompose)
    Int_t global;          // --global G: strong scaling, local brick = G/p per axis
    Int_t syncEvery;       // --sync-every K cycles between host polls
+   Int_t deviceSetup;     // --device-setup: lulesh_b200_create_sedov instead of a host Domain
 };

@@ -50,6 +50,7 @@ void PrintCommandLineOptions(char *execname)
    printf(" --decomp AxBxC  : B200 extension: ranks per axis (col x row x plane)\n");
    printf(" --global <size> : B200 extension: -s is the GLOBAL edge, split over the ranks\n");
    printf(" --sync-every <k>: B200 extension: cycles enqueued between host polls (def: 64)\n");
+   printf(" --device-setup  : B200 extension: generate the mesh in HBM instead of on the host\n");
    printf("\n\n");
 }
 
@@ -90,7 +91,8 @@ void ParseCommandLineOptions(int argc, char *argv[], cmdLineOpts *opts)
          if (i + 1 >= argc || sscanf(argv[i + 1], "%dx%dx%d", &opts->px, &opts->py, &opts->pz) != 3)
             ParseError("Parse Error on option --decomp AxBxC required after argument\n");
          i += 2;
-      } else if (strcmp(argv[i], "-p") == 0) { opts->showProg = 1; i++; }
+      } else if (strcmp(argv[i], "--device-setup") == 0) { opts->deviceSetup = 1; i++; }
+      else if (strcmp(argv[i], "-p") == 0) { opts->showProg = 1; i++; }
       else if (strcmp(argv[i], "-q") == 0) { opts->quiet = 1; i++; }
       else if (strcmp(argv[i], "-v") == 0) {
          ParseError("Use of -v requires compiling with -DVIZ_MESH\n");   // lulesh-util.cc:146-152
@@ -109,7 +111,17 @@ void ParseCommandLineOptions(int argc, char *argv[], cmdLineOpts *opts)
 // ---- lulesh-util.cc:175-230, reading e() from the host Domain after download.
 // `zones` is the true global zone count (nx^3*numRanks for the reference's
 // cubic layouts); `n` is the edge of the square part of rank 0's plane 0.
-void VerifyAndWriteFinalOutput(Real_t elapsed_time, Domain &locDom, Int_t nx, Int_t numRanks,
+struct ReportView {   // what the final report reads from rank 0's Domain
+   Int_t cycles;
+   const Real_t *energy;   // e(i), i < sizeX*sizeY is enough
+   Index_t sx, sy;
+   Int_t cycle() const { return cycles; }
+   Real_t e(Index_t i) const { return energy[i]; }
+   Index_t sizeX() const { return sx; }
+   Index_t sizeY() const { return sy; }
+};
+
+void VerifyAndWriteFinalOutput(Real_t elapsed_time, const ReportView &locDom, Int_t nx, Int_t numRanks,
                                long long zones)
 {
    const Real_t perDom = Real_t(zones) / Real_t(numRanks);
@@ -244,10 +256,21 @@ extern "C" int lulesh_host_main(int argc, char **argv)
    auto body = [&](int r) {
       RankState &st = ranks[r];
       // lulesh.cc:2712-2716 (InitMeshDecomp + new Domain)
-      st.dom.reset(new Domain(numRanks, r, opts.px, opts.py, opts.pz, sx, sy, sz, opts.numReg,
-                              opts.balance, opts.cost));
-      lulesh_b200_host_view view = st.dom->view();
-      st.status = lulesh_b200_create(&view, r, numRanks > 1 ? uid : NULL, &st.handle);
+      if (opts.deviceSetup) {   // mesh, connectivity, BCs, masses generated by kernels in HBM
+         lulesh_b200_sedov_params sp;
+         memset(&sp, 0, sizeof sp);
+         sp.abi_version = LULESH_B200_ABI_VERSION;
+         sp.numRanks = numRanks; sp.rank = r;
+         sp.px = opts.px; sp.py = opts.py; sp.pz = opts.pz;
+         sp.sx = sx; sp.sy = sy; sp.sz = sz;
+         sp.numReg = opts.numReg; sp.balance = opts.balance; sp.cost = opts.cost;
+         st.status = lulesh_b200_create_sedov(&sp, r, numRanks > 1 ? uid : NULL, &st.handle);
+      } else {
+         st.dom.reset(new Domain(numRanks, r, opts.px, opts.py, opts.pz, sx, sy, sz, opts.numReg,
+                                 opts.balance, opts.cost));
+         lulesh_b200_host_view view = st.dom->view();
+         st.status = lulesh_b200_create(&view, r, numRanks > 1 ? uid : NULL, &st.handle);
+      }
       if (st.status == 0) st.status = lulesh_b200_sum_nodal_mass(st.handle);   // lulesh.cc:2720-2732
       if (st.status != 0) fprintf(stderr, "lulesh_b200 (rank %d): %s\n", r, lulesh_b200_last_error());
       pthread_barrier_wait(&barrier);
@@ -280,12 +303,16 @@ extern "C" int lulesh_host_main(int argc, char **argv)
    if (status != 0) return 1;
 
    if (opts.quiet == 0) {   // lulesh.cc:2781-2783
-      Domain &d0 = *ranks[0].dom;
       lulesh_b200_scalars s;
       lulesh_b200_get_scalars(ranks[0].handle, &s);
-      d0.scalars() = s;
-      lulesh_b200_download(ranks[0].handle, LULESH_F_E, &d0.e(0), d0.numElem());
-      VerifyAndWriteFinalOutput(elapsed, d0, opts.nx, numRanks, zones);
+      std::vector<Real_t> e((size_t)sx * sy * sz);
+      lulesh_b200_download(ranks[0].handle, LULESH_F_E, e.data(), e.size());
+      if (ranks[0].dom) {   // keep the host Domain in step with the device, as a caller would
+         ranks[0].dom->scalars() = s;
+         std::copy(e.begin(), e.end(), &ranks[0].dom->e(0));
+      }
+      const ReportView rv = {s.cycle, e.data(), sx, sy};
+      VerifyAndWriteFinalOutput(elapsed, rv, opts.nx, numRanks, zones);
    }
    for (RankState &st : ranks) lulesh_b200_destroy(st.handle);
    pthread_barrier_destroy(&barrier);

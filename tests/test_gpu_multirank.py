@@ -17,7 +17,7 @@ def ngpu():
     return torch.cuda.device_count()
 
 
-def run_ranks(lb, decomp, sizes, its, num_reg=11, balance=1, cost=1, expect_mode=None):
+def run_ranks(lb, decomp, sizes, its, num_reg=11, balance=1, cost=1, expect_mode=None, device_setup=False):
     n = decomp[0] * decomp[1] * decomp[2]
     uid = lb.get_unique_id()
     out, errs = [None] * n, []
@@ -25,7 +25,11 @@ def run_ranks(lb, decomp, sizes, its, num_reg=11, balance=1, cost=1, expect_mode
     def body(r):
         try:
             dom = lb.Domain(sizes[0], num_reg, balance, cost, num_ranks=n, rank=r, decomp=decomp, sizes=sizes)
-            dev = lb.Device(dom, device=r, unique_id=uid)
+            if device_setup:
+                dev = lb.Device.sedov(sizes[0], num_reg, balance, cost, num_ranks=n, rank=r, decomp=decomp,
+                                      sizes=sizes, device=r, unique_id=uid)
+            else:
+                dev = lb.Device(dom, device=r, unique_id=uid)
             dev.sum_nodal_mass()
             if expect_mode:
                 assert dev.halo_mode == expect_mode, dev.halo_mode
@@ -116,6 +120,17 @@ def test_eight_ranks_against_reference_mpi_build(lb, goldens):
     for name, key in (("e", "sum_e"), ("p", "sum_p"), ("q", "sum_q"), ("v", "sum_v")):
         assert abs(float(np.sum(r0[name])) - gold[key]) <= 1e-9 * abs(gold[key]) + 1e-12, name
     assert [len(r0["dom"].region_list(i)) for i in range(11)] == gold["regions"]
+
+
+def test_device_side_setup_multi_rank(lb):
+    """Device-generated bricks (incl. COMM flags, ghost indices, per-rank regions) == host Domains."""
+    if ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    a = run_ranks(lb, (1, 1, 2), (10, 10, 5), 60)
+    b = run_ranks(lb, (1, 1, 2), (10, 10, 5), 60, device_setup=True)
+    for ra, rb in zip(a, b):
+        for f in "x y z xd yd zd e p q v nodalMass".split():
+            assert np.array_equal(ra[f], rb[f]), f
 
 
 def test_two_rank_driver_binary(lb, goldens):

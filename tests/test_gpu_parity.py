@@ -236,6 +236,23 @@ def test_full_size_properties_s128(lb):
     dev.close(); dev2.close()
 
 
+@pytest.mark.parametrize("kw", [dict(nx=9), dict(nx=14, num_reg=16, balance=1, cost=8), dict(nx=1)])
+def test_device_side_setup_equals_host_domain(lb, kw):
+    """lulesh_b200_create_sedov (mesh, corner table, connectivity, BCs, masses generated by
+    kernels in HBM) against the upload of the host Domain: identical arrays, identical run."""
+    a = lb.Device(lb.Domain(**kw))
+    b = lb.Device.sedov(**kw)
+    for f in "x y z xd yd zd nodalMass e p q v volo ss elemMass".split():
+        assert np.array_equal(a.download(f), b.download(f)), f
+    sa, sb = a.scalars, b.scalars
+    assert all(getattr(sa, n) == getattr(sb, n) for n, _ in lb.Scalars._fields_)
+    a.run(40); b.run(40)
+    for f in "x y z xd yd zd e p q v ss".split():
+        assert np.array_equal(a.download(f), b.download(f)), f
+    assert a.scalars.time == b.scalars.time and a.scalars.cycle == b.scalars.cycle
+    a.close(); b.close()
+
+
 def test_driver_binary_report(lb, goldens):
     p = subprocess.run([lb.BIN_PATH, "-s", "10"], capture_output=True, text=True,
                        env={"LULESH_B200_FULL_PRECISION": "1", "PATH": "/usr/bin:/bin"})
@@ -248,6 +265,10 @@ def test_driver_binary_report(lb, goldens):
     rec = json.loads([l for l in out.splitlines() if l.startswith("B200JSON ")][0][9:])
     gold = goldens["lulesh_omp -s 10"]
     assert rec["cycles"] == gold["cycles"] and abs(rec["e0"] - gold["e0"]) <= 1e-10 * gold["e0"]
+    ds = subprocess.run([lb.BIN_PATH, "-s", "10", "--device-setup"], capture_output=True, text=True,
+                        env={"LULESH_B200_FULL_PRECISION": "1", "PATH": "/usr/bin:/bin"})
+    rec2 = json.loads([l for l in ds.stdout.splitlines() if l.startswith("B200JSON ")][0][9:])
+    assert rec2["cycles"] == rec["cycles"] and rec2["e0"] == rec["e0"]      # bit-identical setup
     q = subprocess.run([lb.BIN_PATH, "-s", "10", "-q"], capture_output=True, text=True)
     assert q.returncode == 0 and q.stdout == ""
     pr = subprocess.run([lb.BIN_PATH, "-s", "5", "-i", "3", "-p"], capture_output=True, text=True)
