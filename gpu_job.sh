@@ -1,30 +1,22 @@
 mkdir -p gpurun_out
-Q='kernels_one_by_one or cycles_against_oracle or step_equals or deterministic or error_codes'
-run_quick() { # name, env...
-  name=$1; shift
-  (env "$@" timeout 300 python -m pytest tests/test_gpu_parity.py -x -q --timeout 60 -k "$Q" > gpurun_out/quick_$name.log 2>&1; echo "pytest exit $?" >> gpurun_out/quick_$name.log)
-  echo "quick $name: $(tail -n 2 gpurun_out/quick_$name.log | tr '\n' ' ')"
-}
-run_quick nofuse LULESH_B200_FUSE=0
-run_quick fused X=1
-run_quick lag4 LULESH_B200_LIB=$PWD/lulesh_b200/lib/liblulesh_b200_lag4.so
-run_quick fc0 LULESH_B200_LIB=$PWD/lulesh_b200/lib/liblulesh_b200_fc0.so
-if grep -L "pytest exit 0" gpurun_out/quick_*.log | grep -q .; then echo "SOME QUICK TESTS FAILED"; grep -L "pytest exit 0" gpurun_out/quick_*.log; fi
-bench() { # name size env...
-  name=$1; s=$2; shift 2
-  env "$@" timeout 300 python bench.py --size $s --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/b_${name}_s$s.json 2> gpurun_out/b_${name}_s$s.err
-  python - <<PY
-import json
-try:
-    d=json.loads(open("gpurun_out/b_${name}_s$s.json").read().strip().splitlines()[-1])
-    print("$name s$s", round(d["value"]/1e9,3), "G  ms", round(d["ms_per_step"],4), {k:round(x,4) for k,x in d["roofline"]["per_kernel_ms"].items()})
-except Exception as e:
-    print("$name s$s FAILED", e)
+free -g | head -n 2 > gpurun_out/host.txt; nproc >> gpurun_out/host.txt; lscpu | grep "Model name" >> gpurun_out/host.txt
+(python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log)
+(timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu_full.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_full.log)
+tail -n 3 gpurun_out/smoke.log; tail -n 3 gpurun_out/pytest_gpu_full.log
+python bench.py --impl reference > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err
+python bench.py > gpurun_out/final_s128.json 2> gpurun_out/final_s128.err
+python bench.py --size 256 --steps 60 --warmup 5 > gpurun_out/final_s256.json 2> gpurun_out/final_s256.err
+python bench.py --size 256 --regions 16 --balance 1 --cost 8 --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/final_cfg3.json 2> gpurun_out/final_cfg3.err
+python bench.py --size 320 --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/final_s320.json 2> gpurun_out/final_s320.err
+ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 50 --csv --log-file gpurun_out/final_launches_s128.csv python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_force|k_kinematics|k_material|k_node" -s 40 -c 4 -f -o gpurun_out/prof_s128_final python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_final.log 2>&1
+ncu --set full --clock-control none -k regex:"k_force|k_kinematics|k_material|k_node" -s 16 -c 4 -f -o gpurun_out/prof_s256_final python bench.py --size 256 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_final256.log 2>&1
+cat gpurun_out/host.txt
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/final_*.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1]); r=d.get("roofline") or {}
+        print(f, round(d["value"]/1e9,4), round(d["ms_per_step"],4), {k:round(v,4) for k,v in (r.get("per_kernel_ms") or {}).items()}, "e2e", round(d["e2e"]["value"]/1e9,3), "roof", round(r.get("frac",0),3), "step", round((r.get("step") or {}).get("frac",0),3), d.get("cpu_baseline"), d.get("clocks"))
+    except Exception as e: print(f, "ERR", e, open(f.replace('.json','.err')).read()[-300:])
 PY
-}
-bench nofuse 128 LULESH_B200_FUSE=0
-bench fused 128 X=1
-bench lag4 128 LULESH_B200_LIB=$PWD/lulesh_b200/lib/liblulesh_b200_lag4.so
-bench fc0 128 LULESH_B200_LIB=$PWD/lulesh_b200/lib/liblulesh_b200_fc0.so
-bench nofuse 256 LULESH_B200_FUSE=0
-bench lag4 256 LULESH_B200_LIB=$PWD/lulesh_b200/lib/liblulesh_b200_lag4.so
