@@ -136,8 +136,9 @@ def run_reference(size, cycles, regions=(11, 1, 1), nranks=1):
 
 
 def reference_cycle_budget(size, steps, seconds=60.0):
-    # ~2.5e6 zone-cycles/s is typical for the OpenMP reference on 8 host cores
-    per_cycle = float(size) ** 3 / 2.0e6
+    # the OpenMP reference does ~0.55e6 zone-cycles/s per host core (8.5-11.9e6 measured on the
+    # 16-core GPU boxes, 2.5e6 on 8 slower cores in BASELINE.md)
+    per_cycle = float(size) ** 3 / (0.55e6 * (os.cpu_count() or 1))
     return max(2, min(steps, int(seconds / per_cycle)))
 
 
@@ -147,7 +148,7 @@ def impl_reference(args):
         return 0
     cube = round(args.gpus ** (1.0 / 3.0)) ** 3 == args.gpus
     nranks = args.gpus if (args.gpus > 1 and cube) else 1
-    cycles = reference_cycle_budget(args.size, args.steps + args.warmup, 120.0 / nranks)
+    cycles = reference_cycle_budget(args.size, args.steps + args.warmup, 60.0 / nranks)
     t0 = time.time()
     zcs, cores, kind, sample = run_reference(args.size, cycles, (args.regions, args.balance, args.cost), nranks)
     line = {
@@ -163,7 +164,7 @@ def impl_reference(args):
                 "domain; for cubic rank counts its USE_MPI=1 build under a single-node MPI stand-in "
                 "(oracle/mpishim; the image has no MPI); 2 and 4 ranks do not exist in the reference",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -178,7 +179,28 @@ def workload_config(args, n):
             "l2_policy": "working set per cycle (>= 1.1 GB at -s 128) exceeds the 126 MB L2; no flush needed"}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL (version banner, NCCL_DEBUG output) and other
+    native libraries write to file descriptor 1 directly, so fd 1 is pointed at stderr for the
+    whole run and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
@@ -330,7 +352,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            cyc = reference_cycle_budget(args.size, 10**9, 20.0)
+            cyc = reference_cycle_budget(args.size, 10**9, 15.0)
             zcs, cores, kind, sample = run_reference(args.size, cyc, (args.regions, args.balance, args.cost))
             cpu = {"value": zcs, "unit": "zones/s", "cores": cores, "kind": kind, "sample": sample}
         except Exception as ex:  # the baseline is reported, never required for the GPU number
@@ -347,7 +369,7 @@ def main():
         "clocks": clocks,
         "state": {"cycle": s_end.cycle, "time": s_end.time, "dt": s_end.deltatime},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
