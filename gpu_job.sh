@@ -1,22 +1,25 @@
 mkdir -p gpurun_out
-free -g | head -n 2 > gpurun_out/host.txt; nproc >> gpurun_out/host.txt; lscpu | grep "Model name" >> gpurun_out/host.txt
-(python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log)
-(timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu_full.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_full.log)
-tail -n 3 gpurun_out/smoke.log; tail -n 3 gpurun_out/pytest_gpu_full.log
-python bench.py --impl reference > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err
-python bench.py > gpurun_out/final_s128.json 2> gpurun_out/final_s128.err
-python bench.py --size 256 --steps 60 --warmup 5 > gpurun_out/final_s256.json 2> gpurun_out/final_s256.err
-python bench.py --size 256 --regions 16 --balance 1 --cost 8 --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/final_cfg3.json 2> gpurun_out/final_cfg3.err
-python bench.py --size 320 --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/final_s320.json 2> gpurun_out/final_s320.err
-ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 50 --csv --log-file gpurun_out/final_launches_s128.csv python bench.py --steps 10 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_force|k_kinematics|k_material|k_node" -s 40 -c 4 -f -o gpurun_out/prof_s128_final python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_final.log 2>&1
-ncu --set full --clock-control none -k regex:"k_force|k_kinematics|k_material|k_node" -s 16 -c 4 -f -o gpurun_out/prof_s256_final python bench.py --size 256 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_final256.log 2>&1
-cat gpurun_out/host.txt
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob("gpurun_out/final_*.json")):
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1]); r=d.get("roofline") or {}
-        print(f, round(d["value"]/1e9,4), round(d["ms_per_step"],4), {k:round(v,4) for k,v in (r.get("per_kernel_ms") or {}).items()}, "e2e", round(d["e2e"]["value"]/1e9,3), "roof", round(r.get("frac",0),3), "step", round((r.get("step") or {}).get("frac",0),3), d.get("cpu_baseline"), d.get("clocks"))
-    except Exception as e: print(f, "ERR", e, open(f.replace('.json','.err')).read()[-300:])
+nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
+run() { # name n env...
+  name=$1; n=$2; shift 2
+  if [ "$n" = 1 ]; then
+    env "$@" timeout 300 python bench.py --gpus 1 --no-cpu-baseline > gpurun_out/scale2_$name.json 2> gpurun_out/scale2_$name.err
+  else
+    env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) bench.py --gpus $n --no-cpu-baseline > gpurun_out/scale2_$name.json 2> gpurun_out/scale2_$name.err
+  fi
+  python - <<PY
+import json
+try:
+    txt=open("gpurun_out/scale2_$name.json").read().strip().splitlines()
+    d=json.loads(txt[-1])
+    print("$name", "lines", len(txt), round(d["value"]/1e9,3), "G  ms", round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"]/1e9,3), d["config"].get("halo"), d["clocks"])
+except Exception as e:
+    print("$name FAILED", e); print(open("gpurun_out/scale2_$name.err").read()[-500:])
 PY
+}
+run n2_a 2 X=1
+run n8 8 X=1
+run n2_b 2 X=1
+run n4 4 X=1
+run n2_nccl 2 LULESH_B200_HALO=nccl
+run n1 1 X=1
