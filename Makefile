@@ -30,7 +30,7 @@ $(OBJ)/%.o: $(CSRC)/host/%.cc $(CSRC)/host/domain.h include/lulesh_b200.h includ
 	@mkdir -p $(OBJ)
 	$(HOSTCXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(OBJ)/kernels.o $(OBJ)/api.o $(OBJ)/setup.o $(OBJ)/domain.o $(OBJ)/host_capi.o $(OBJ)/driver.o
+$(LIB): $(OBJ)/kernels.o $(OBJ)/api.o $(OBJ)/setup.o $(OBJ)/domain.o $(OBJ)/host_capi.o $(OBJ)/driver.o $(OBJ)/vizdump.o
 	@mkdir -p lulesh_b200/lib
 	$(NVCC) $(ARCH) -shared -cudart static -ccbin $(HOSTCXX) -o $@ $^ -ldl -lpthread
 

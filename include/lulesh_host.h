@@ -33,6 +33,13 @@ double *lulesh_host_domain_field(lulesh_host_domain *d, int field, size_t *count
 const int32_t *lulesh_host_domain_ints(lulesh_host_domain *d, const char *name, size_t *count);
 lulesh_b200_scalars *lulesh_host_domain_scalars(lulesh_host_domain *d);
 
+/* The `-v` dump of one rank's Domain (DumpToVisit / DumpDomainToVisit,
+ * lulesh-viz.cc:56-258): mesh, connectivity, region numbers, zone fields e p v q,
+ * node fields speed xd yd zd -- as a binary legacy-VTK unstructured grid instead of
+ * Silo.  The Domain's host arrays are written as they are (the driver downloads the
+ * device state into them first).  Returns 0 on success, -1 on I/O errors. */
+int lulesh_host_domain_write_vtk(lulesh_host_domain *d, int rank, const char *path);
+
 /* InitMeshDecomp (lulesh-init.cc:676-738) generalised: picks (px,py,pz) for
  * numRanks in {1,2,4,8,27,...}: cubes as the reference, 2 -> 1x1x2, 4 -> 1x2x2.
  * Returns 0 on success. */

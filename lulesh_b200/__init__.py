@@ -93,7 +93,7 @@ ABI_SYMBOLS = (
     "lulesh_b200_destroy "
     "lulesh_host_domain_new lulesh_host_domain_free lulesh_host_domain_view "
     "lulesh_host_domain_field lulesh_host_domain_ints lulesh_host_domain_scalars "
-    "lulesh_host_decompose lulesh_host_main").split()
+    "lulesh_host_domain_write_vtk lulesh_host_decompose lulesh_host_main").split()
 
 
 def _sig(name, restype, *argtypes):
@@ -135,6 +135,7 @@ _sig("lulesh_host_domain_view", None, _vp, C.POINTER(HostView))
 _sig("lulesh_host_domain_field", _pd, _vp, C.c_int, C.POINTER(C.c_size_t))
 _sig("lulesh_host_domain_ints", _pi, _vp, C.c_char_p, C.POINTER(C.c_size_t))
 _sig("lulesh_host_domain_scalars", C.POINTER(Scalars), _vp)
+_sig("lulesh_host_domain_write_vtk", C.c_int, _vp, C.c_int, C.c_char_p)
 _sig("lulesh_host_decompose", C.c_int, C.c_int, *([C.POINTER(C.c_int)] * 3))
 _sig("lulesh_host_main", C.c_int, C.c_int, C.POINTER(C.c_char_p))
 
@@ -207,6 +208,11 @@ class Domain:
     def refresh_view(self):
         _lib.lulesh_host_domain_view(self._p, C.byref(self.view))
         return self.view
+
+    def write_vtk(self, path, rank=0):
+        """The `-v` dump of this Domain's host arrays (lulesh-viz.cc:56-258, VTK instead of Silo)."""
+        if _lib.lulesh_host_domain_write_vtk(self._p, rank, os.fsencode(path)) != 0:
+            raise OSError(f"cannot write {path}")
 
     def __del__(self):
         if getattr(self, "_p", None):

@@ -153,6 +153,10 @@ void SedovInitialScalars(Index_t globalEdge, lulesh_b200_scalars *s, lulesh_b200
 // CalcElemVolume (lulesh.cc:1274-1366), needed by the setup for volo/elemMass.
 Real_t CalcElemVolume(const Real_t x[8], const Real_t y[8], const Real_t z[8]);
 
+// `-v` field dump (lulesh-viz.cc:56-258 with VTK in place of Silo), vizdump.cc
+int DumpDomainToVTK(Domain &d, Int_t myRank, const char *path);
+int WriteVisitIndex(const char *path, const char *basename, Int_t numRanks);
+
 struct cmdLineOpts {   // lulesh.h:599-609 plus the additive multi-GPU flags
    Int_t its, nx, numReg, numFiles, showProg, quiet, viz, cost, balance;
    Int_t gpus;            // --gpus N   (ranks = GPUs of this node, one host thread each)

@@ -44,7 +44,7 @@ void PrintCommandLineOptions(char *execname)
    printf(" -c <cost>       : Extra cost of more expensive regions (def: 1)\n");
    printf(" -f <numfiles>   : Number of files to split viz dump into (def: (np+10)/9)\n");
    printf(" -p              : Print out progress\n");
-   printf(" -v              : Output viz file (requires compiling with -DVIZ_MESH\n");
+   printf(" -v              : Output viz file (VTK, one per rank; no -DVIZ_MESH/Silo needed)\n");
    printf(" -h              : This message\n");
    printf(" --gpus <n>      : B200 extension: ranks = GPUs of this node (def: 1)\n");
    printf(" --decomp AxBxC  : B200 extension: ranks per axis (col x row x plane)\n");
@@ -94,9 +94,8 @@ void ParseCommandLineOptions(int argc, char *argv[], cmdLineOpts *opts)
       } else if (strcmp(argv[i], "--device-setup") == 0) { opts->deviceSetup = 1; i++; }
       else if (strcmp(argv[i], "-p") == 0) { opts->showProg = 1; i++; }
       else if (strcmp(argv[i], "-q") == 0) { opts->quiet = 1; i++; }
-      else if (strcmp(argv[i], "-v") == 0) {
-         ParseError("Use of -v requires compiling with -DVIZ_MESH\n");   // lulesh-util.cc:146-152
-      } else if (strcmp(argv[i], "-h") == 0) {
+      else if (strcmp(argv[i], "-v") == 0) { opts->viz = 1; i++; }   // lulesh-util.cc:146-152 with VIZ_MESH
+      else if (strcmp(argv[i], "-h") == 0) {
          PrintCommandLineOptions(argv[0]);
          exit(0);
       } else {
@@ -313,6 +312,38 @@ extern "C" int lulesh_host_main(int argc, char **argv)
       }
       const ReportView rv = {s.cycle, e.data(), sx, sy};
       VerifyAndWriteFinalOutput(elapsed, rv, opts.nx, numRanks, zones);
+   }
+   if (opts.viz) {   // lulesh.cc:2776-2778 (DumpToVisit); -f is accepted, the dump is one block per rank
+      lulesh_b200_scalars s;
+      lulesh_b200_get_scalars(ranks[0].handle, &s);
+      char basename[32], name[64];
+      snprintf(basename, sizeof basename, "lulesh_plot_c%d", s.cycle);   // lulesh-viz.cc:62
+      static const int dumped[] = {LULESH_F_X, LULESH_F_Y, LULESH_F_Z, LULESH_F_XD, LULESH_F_YD,
+                                   LULESH_F_ZD, LULESH_F_E, LULESH_F_P, LULESH_F_V, LULESH_F_Q};
+      for (int r = 0; r < numRanks; ++r) {
+         RankState &st = ranks[r];
+         if (!st.dom)   // device-side setup keeps no host mesh: rebuild it for the connectivity
+            st.dom.reset(new Domain(numRanks, r, opts.px, opts.py, opts.pz, sx, sy, sz, opts.numReg,
+                                    opts.balance, opts.cost));
+         st.dom->scalars() = s;
+         for (int fld : dumped) {
+            std::vector<Real_t> *a = st.dom->realField(fld);
+            if (lulesh_b200_download(st.handle, fld, a->data(), a->size()) != 0) {
+               fprintf(stderr, "lulesh_b200 (rank %d): %s\n", r, lulesh_b200_last_error());
+               return 1;
+            }
+         }
+         snprintf(name, sizeof name, "%s.%03d.vtk", basename, r);
+         if (DumpDomainToVTK(*st.dom, r, name) != 0) {
+            fprintf(stderr, "lulesh_b200: cannot write %s\n", name);
+            return 1;
+         }
+      }
+      snprintf(name, sizeof name, "%s.visit", basename);
+      if (WriteVisitIndex(name, basename, numRanks) != 0) {
+         fprintf(stderr, "lulesh_b200: cannot write %s\n", name);
+         return 1;
+      }
    }
    for (RankState &st : ranks) lulesh_b200_destroy(st.handle);
    pthread_barrier_destroy(&barrier);

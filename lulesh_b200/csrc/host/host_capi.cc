@@ -44,3 +44,9 @@ extern "C" lulesh_b200_scalars *lulesh_host_domain_scalars(lulesh_host_domain *d
 {
    return &d->dom.scalars();
 }
+
+extern "C" int lulesh_host_domain_write_vtk(lulesh_host_domain *d, int rank, const char *path)
+{
+   if (!d || !path) return -1;
+   return DumpDomainToVTK(d->dom, rank, path);
+}

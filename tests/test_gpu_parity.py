@@ -274,3 +274,20 @@ def test_driver_binary_report(lb, goldens):
     pr = subprocess.run([lb.BIN_PATH, "-s", "5", "-i", "3", "-p"], capture_output=True, text=True)
     assert "cycle = 1, time = 3.417997e-04, dt=3.417997e-04" in pr.stdout
     assert "cycle = 3, time = 8.925464e-04, dt=1.405871e-04" in pr.stdout
+
+
+def test_driver_viz_dump(lb, tmp_path):
+    """`-v`: one VTK block per rank + a .visit index after the run (lulesh.cc:2776-2778)."""
+    from test_host_domain import read_vtk
+    for extra in ([], ["--device-setup"]):
+        p = subprocess.run([lb.BIN_PATH, "-s", "6", "-i", "12", "-v", "-q", *extra], capture_output=True,
+                           text=True, cwd=tmp_path)
+        assert p.returncode == 0, p.stderr
+        assert (tmp_path / "lulesh_plot_c12.visit").read_text() == "!NBLOCKS 1\nlulesh_plot_c12.000.vtk\n"
+        vtk = read_vtk(tmp_path / "lulesh_plot_c12.000.vtk")
+        dev = lb.Device(lb.Domain(6))
+        dev.run(12)
+        for name in "e p v q xd yd zd".split():
+            assert np.array_equal(vtk[name], dev.download(name)), name
+        assert np.array_equal(vtk["points"][:, 0], dev.download("x"))
+        dev.close()

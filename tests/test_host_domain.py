@@ -129,8 +129,7 @@ def test_cli_help_and_errors(lb):
     p = _cli(lb, "-i", "2x")
     assert p.returncode == 255
     assert "Parse Error on option -i integer value required after argument" in p.stdout
-    p = _cli(lb, "-v")
-    assert p.returncode == 255 and "Use of -v requires compiling with -DVIZ_MESH" in p.stdout
+    assert " -v              : Output viz file" in _cli(lb, "-h").stdout
 
 
 def test_create_rejects_bad_views_before_touching_the_gpu(lb):
@@ -158,3 +157,72 @@ def test_create_rejects_bad_views_before_touching_the_gpu(lb):
     assert lb._lib.lulesh_b200_run(None, 1, 1, lb.PROGRESS_CB(), None) == lb.EINVAL
     assert lb._lib.lulesh_b200_field_count(None, 0) == 0
     lb._lib.lulesh_b200_destroy(None)
+
+
+def read_vtk(path):
+    """Minimal reader of the binary legacy-VTK files written by vizdump.cc."""
+    raw = open(path, "rb").read()
+    pos = 0
+
+    def line():
+        nonlocal pos
+        end = raw.index(b"\n", pos)
+        out = raw[pos:end].decode()
+        pos = end + 1
+        return out
+
+    def block(dtype, count):
+        nonlocal pos
+        a = np.frombuffer(raw, dtype=dtype, count=count, offset=pos)
+        pos += a.nbytes
+        assert raw[pos:pos + 1] == b"\n"
+        pos += 1
+        return a
+
+    out = {"header": [line() for _ in range(4)]}
+    tok = line().split()
+    assert tok[0] == "POINTS" and tok[2] == "double"
+    nn = int(tok[1])
+    out["points"] = block(">f8", 3 * nn).reshape(nn, 3)
+    tok = line().split()
+    assert tok[0] == "CELLS"
+    ne = int(tok[1])
+    assert int(tok[2]) == 9 * ne
+    out["cells"] = block(">i4", 9 * ne).reshape(ne, 9)
+    assert line().split() == ["CELL_TYPES", str(ne)]
+    out["cell_types"] = block(">i4", ne)
+    for section, n in (("CELL_DATA", ne), ("POINT_DATA", nn)):
+        assert line().split() == [section, str(n)]
+        while pos < len(raw) and raw[pos:pos + 7] == b"SCALARS":
+            _, name, typ, _one = line().split()
+            assert line() == "LOOKUP_TABLE default"
+            out[name] = block(">f8" if typ == "double" else ">i4", n)
+    assert pos == len(raw)
+    return out
+
+
+def test_viz_dump_holds_the_reference_field_set(lb, tmp_path):
+    """`-v` (lulesh-viz.cc:121-258): mesh, connectivity, regions, e p v q, speed xd yd zd."""
+    dom = lb.Domain(5, 4, 1, 1, num_ranks=8, rank=7)
+    dom.field("xd")[:] = np.linspace(-1.0, 2.0, dom.numNode)
+    dom.field("yd")[:] = 0.5
+    dom.field("p")[:] = np.arange(dom.numElem) * 0.25
+    dom.scalars.cycle = 42
+    path = tmp_path / "lulesh_plot_c42.007.vtk"
+    dom.write_vtk(path, rank=7)
+    vtk = read_vtk(path)
+    assert vtk["header"][0] == "# vtk DataFile Version 3.0" and "cycle 42" in vtk["header"][1]
+    assert "rank 7" in vtk["header"][1] and vtk["header"][2:] == ["BINARY", "DATASET UNSTRUCTURED_GRID"]
+    for c, name in enumerate("xyz"):
+        assert np.array_equal(vtk["points"][:, c], dom.field(name))
+    assert np.all(vtk["cells"][:, 0] == 8) and np.all(vtk["cell_types"] == 12)   # VTK_HEXAHEDRON
+    assert np.array_equal(vtk["cells"][:, 1:].ravel(), dom.ints("nodelist"))
+    for name in "e p v q".split():
+        assert np.array_equal(vtk[name], dom.field(name)), name
+    assert np.array_equal(vtk["regions"], dom.ints("regNumList"))
+    for name in "xd yd zd".split():
+        assert np.array_equal(vtk[name], dom.field(name)), name
+    speed = np.sqrt(dom.field("xd") ** 2 + dom.field("yd") ** 2 + dom.field("zd") ** 2)
+    assert np.allclose(vtk["speed"], speed, rtol=1e-15)
+    with pytest.raises(OSError):
+        dom.write_vtk(tmp_path / "missing_dir" / "x.vtk")
