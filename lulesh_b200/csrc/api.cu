@@ -69,19 +69,15 @@ struct NcclApi {
    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 };
 
-static NcclApi *nccl_api()
+static bool load_nccl(NcclApi &api)
 {
-   static NcclApi api;
-   static bool tried = false;
-   if (tried) return api.lib ? &api : nullptr;
-   tried = true;
    const char *names[] = {"libnccl.so.2", "libnccl.so"};
    for (const char *n : names)
       if ((api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
-   if (!api.lib) return nullptr;
+   if (!api.lib) return false;
 #define SYM(field, name)                                                      \
    *(void **)(&api.field) = dlsym(api.lib, name);                             \
-   if (!api.field) { api.lib = nullptr; return nullptr; }
+   if (!api.field) { api.lib = nullptr; return false; }
    SYM(GetUniqueId, "ncclGetUniqueId")
    SYM(CommInitRank, "ncclCommInitRank")
    SYM(CommDestroy, "ncclCommDestroy")
@@ -93,7 +89,16 @@ static NcclApi *nccl_api()
    SYM(GetErrorString, "ncclGetErrorString")
    SYM(AllGather, "ncclAllGather")
 #undef SYM
-   return &api;
+   return true;
+}
+
+static NcclApi *nccl_api()
+{
+   // one load per process; the driver creates its handles from one thread per GPU, and the
+   // initialisation of a function-local static is thread-safe
+   static NcclApi api;
+   static const bool ok = load_nccl(api);
+   return ok ? &api : nullptr;
 }
 
 #define NK(call)                                                                      \
@@ -270,11 +275,9 @@ extern "C" int lulesh_b200_get_unique_id(void *out_id)
 static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void *unique_id,
                       std::vector<unsigned char> &nodeFlags);
 
-// `gen` != NULL: device-side Sedov setup (lulesh_b200_create_sedov): the view carries sizes,
-// decomposition, constants, scalars and the region lists only; every other array is generated
-// in HBM by the kernels of setup.cu.
-static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int device,
-                       const void *unique_id, const SetupParams *gen)
+// Everything create() can check without a GPU.  The kernels index with the connectivity,
+// neighbour, corner and region arrays unchecked, so anything out of range is rejected here.
+static int validate_view(const lulesh_b200_host_view *v, bool generated)
 {
    if (v->abi_version != LULESH_B200_ABI_VERSION)
       return fail(LULESH_B200_EINVAL, "abi_version %d != %d", v->abi_version, LULESH_B200_ABI_VERSION);
@@ -282,14 +285,66 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    if (ne <= 0 || nn <= 0 || (long long)v->sizeX * v->sizeY * v->sizeZ != ne ||
        (long long)(v->sizeX + 1) * (v->sizeY + 1) * (v->sizeZ + 1) != nn)
       return fail(LULESH_B200_EINVAL, "inconsistent sizes in host view");
+   if ((long long)ne + 15 > INT_MAX / 8 || (long long)nn + 31 > INT_MAX / 8)
+      return fail(LULESH_B200_EINVAL, "brick too large for int32 indices");
    if (v->numRanks < 1 || v->px * v->py * v->pz != v->numRanks || v->rank < 0 || v->rank >= v->numRanks)
       return fail(LULESH_B200_EINVAL, "inconsistent decomposition in host view");
    if (!v->regElemSize || !v->regElemlist || v->numReg < 1 ||
-       (!gen && (!v->x || !v->y || !v->z || !v->xd || !v->yd || !v->zd || !v->nodalMass || !v->nodelist ||
-                 !v->lxim || !v->lxip || !v->letam || !v->letap || !v->lzetam || !v->lzetap || !v->elemBC ||
-                 !v->e || !v->p || !v->q || !v->v || !v->volo || !v->ss || !v->elemMass ||
-                 !v->nodeElemStart || !v->nodeElemCornerList)))
+       (!generated && (!v->x || !v->y || !v->z || !v->xd || !v->yd || !v->zd || !v->nodalMass || !v->nodelist ||
+                       !v->lxim || !v->lxip || !v->letam || !v->letap || !v->lzetam || !v->lzetap || !v->elemBC ||
+                       !v->e || !v->p || !v->q || !v->v || !v->volo || !v->ss || !v->elemMass ||
+                       !v->nodeElemStart || !v->nodeElemCornerList)))
       return fail(LULESH_B200_EINVAL, "null array in host view");
+
+   // region lists: a partition of the elements (lulesh-init.cc:401-510)
+   std::vector<char> seen(ne, 0);
+   long long total = 0;
+   for (int r = 0; r < v->numReg; ++r) {
+      const int n = v->regElemSize[r];
+      if (n < 0 || (n > 0 && !v->regElemlist[r])) return fail(LULESH_B200_EINVAL, "bad region list %d", r);
+      total += n;
+      for (int t = 0; t < n; ++t) {
+         const int el = v->regElemlist[r][t];
+         if (el < 0 || el >= ne) return fail(LULESH_B200_EINVAL, "region list entry out of range");
+         if (seen[el]++) return fail(LULESH_B200_EINVAL, "element %d is in more than one region list", el);
+      }
+   }
+   if (total != ne) return fail(LULESH_B200_EINVAL, "region lists cover %lld of %d elements", total, ne);
+   if (generated) return 0;
+
+   const int allElem = ne + 2 * v->sizeX * v->sizeY + 2 * v->sizeX * v->sizeZ + 2 * v->sizeY * v->sizeZ;
+   for (size_t i = 0; i < (size_t)8 * ne; ++i)
+      if (v->nodelist[i] < 0 || v->nodelist[i] >= nn) return fail(LULESH_B200_EINVAL, "nodelist entry out of range");
+   const int32_t *nbr[6] = {v->lxim, v->lxip, v->letam, v->letap, v->lzetam, v->lzetap};
+   for (const int32_t *a : nbr)
+      for (int i = 0; i < ne; ++i)
+         if (a[i] < 0 || a[i] >= allElem) return fail(LULESH_B200_EINVAL, "face neighbour out of range");
+   const struct { const int32_t *list; int n; } symm[3] = {
+      {v->symmX, v->numSymmX}, {v->symmY, v->numSymmY}, {v->symmZ, v->numSymmZ}};
+   for (const auto &sset : symm) {
+      if (sset.n < 0 || (sset.n > 0 && !sset.list)) return fail(LULESH_B200_EINVAL, "bad symmetry node set");
+      for (int i = 0; i < sset.n; ++i)
+         if (sset.list[i] < 0 || sset.list[i] >= nn) return fail(LULESH_B200_EINVAL, "symmetry node out of range");
+   }
+   for (int n = 0; n < nn; ++n) {   // node -> corner CSR (lulesh-init.cc:295-319)
+      const int b = v->nodeElemStart[n], e = v->nodeElemStart[n + 1];
+      if (b < 0 || e < b || e - b > 8) return fail(LULESH_B200_EINVAL, "node %d has %d corners", n, e - b);
+      for (int k = b; k < e; ++k)
+         if (v->nodeElemCornerList[k] < 0 || v->nodeElemCornerList[k] >= 8 * ne)
+            return fail(LULESH_B200_EINVAL, "corner list entry out of range");
+   }
+   return 0;
+}
+
+// `gen` != NULL: device-side Sedov setup (lulesh_b200_create_sedov): the view carries sizes,
+// decomposition, constants, scalars and the region lists only; every other array is generated
+// in HBM by the kernels of setup.cu.
+static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int device,
+                       const void *unique_id, const SetupParams *gen)
+{
+   int rc;
+   if ((rc = validate_view(v, gen != nullptr))) return rc;
+   const int ne = v->numElem, nn = v->numNode;
 
    int ndev = 0;
    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -321,7 +376,6 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    P.nn_pad = (nn + 31) & ~31;
    P.c = v->constants;
    P.unit_rho0 = (v->constants.refdens == 1.0) ? 1 : 0;
-   int rc;
 
    // ---- control block
    Ctl c0{};

@@ -159,6 +159,72 @@ def test_create_rejects_bad_views_before_touching_the_gpu(lb):
     lb._lib.lulesh_b200_destroy(None)
 
 
+@pytest.mark.parametrize("array,index,value,message", [
+    ("nodelist", 5, -1, b"nodelist entry out of range"),
+    ("nodelist", 17, 10**6, b"nodelist entry out of range"),
+    ("lxip", 3, 10**6, b"face neighbour out of range"),
+    ("lzetam", 0, -2, b"face neighbour out of range"),
+    ("symmY", 1, 10**6, b"symmetry node out of range"),
+    ("nodeElemCornerList", 9, 8 * 64, b"corner list entry out of range"),
+    ("nodeElemStart", 4, 10**6, b"corners"),
+])
+def test_create_rejects_out_of_range_indices(lb, array, index, value, message):
+    """The kernels index with these arrays unchecked; create() must refuse them (no GPU needed)."""
+    import ctypes as C
+    d = lb.Domain(4)
+    a = d.ints(array)
+    saved = int(a[index])
+    a[index] = value
+    try:
+        h = C.c_void_p()
+        assert lb._lib.lulesh_b200_create(C.byref(d.refresh_view()), 0, None, C.byref(h)) == lb.EINVAL
+        assert message in lb._lib.lulesh_b200_last_error()
+        assert not h.value
+    finally:
+        a[index] = saved
+
+
+@pytest.mark.parametrize("num_ranks", [1, 2, 4, 8, 27])
+def test_valid_views_pass_validation_and_then_need_a_gpu(lb, num_ranks):
+    """Every rank's view of every supported decomposition is accepted by the GPU-free checks;
+    in this container create() then stops at the first CUDA call (no CPU fallback)."""
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    for rank in range(num_ranks):
+        d = lb.Domain(3, 5, 1, 2, num_ranks=num_ranks, rank=rank)
+        h = C.c_void_p()
+        uid = C.create_string_buffer(lb.UNIQUE_ID_BYTES)
+        rc = lb._lib.lulesh_b200_create(C.byref(d.refresh_view()), 0, uid, C.byref(h))
+        assert rc == lb.ECUDA, lb._lib.lulesh_b200_last_error()
+        assert b"no CPU fallback" in lb._lib.lulesh_b200_last_error() and not h.value
+
+
+def test_create_rejects_region_lists_that_are_not_a_partition(lb):
+    import ctypes as C
+    d = lb.Domain(4)
+    h = C.c_void_p()
+    nonempty = [r for r in range(d.view.numReg) if d.view.regElemSize[r] > 0]
+    r0 = d.region_list(nonempty[0])
+    saved = int(r0[0])
+    other = int(d.region_list(nonempty[1])[0])
+    r0[0] = other                                   # element listed twice (and one missing)
+    assert lb._lib.lulesh_b200_create(C.byref(d.refresh_view()), 0, None, C.byref(h)) == lb.EINVAL
+    assert b"more than one region list" in lb._lib.lulesh_b200_last_error()
+    r0[0] = 64                                      # past the last element
+    assert lb._lib.lulesh_b200_create(C.byref(d.refresh_view()), 0, None, C.byref(h)) == lb.EINVAL
+    assert b"region list entry out of range" in lb._lib.lulesh_b200_last_error()
+    r0[0] = saved
+    v = lb.HostView.from_buffer_copy(d.refresh_view())
+    sizes = (C.c_int32 * v.numReg)(*[v.regElemSize[r] for r in range(v.numReg)])
+    sizes[nonempty[0]] -= 1                         # one element in no region
+    v.regElemSize = C.cast(sizes, type(v.regElemSize))
+    assert lb._lib.lulesh_b200_create(C.byref(v), 0, None, C.byref(h)) == lb.EINVAL
+    assert b"region lists cover 63 of 64 elements" in lb._lib.lulesh_b200_last_error()
+    assert not h.value
+
+
 def read_vtk(path):
     """Minimal reader of the binary legacy-VTK files written by vizdump.cc."""
     raw = open(path, "rb").read()
