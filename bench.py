@@ -349,8 +349,8 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    cpu = None
-    if not args.no_cpu_baseline:
+    cpu = None   # reported at N=1 only (the reference arm, --impl reference, covers every N)
+    if not args.no_cpu_baseline and n == 1:
         try:
             cyc = reference_cycle_budget(args.size, 10**9, 15.0)
             zcs, cores, kind, sample = run_reference(args.size, cyc, (args.regions, args.balance, args.cost))
