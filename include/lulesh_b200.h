@@ -246,15 +246,6 @@ int lulesh_b200_halo_plan_query(const lulesh_b200_halo_plan *plan, const char *w
                                 const int32_t **data, size_t *count);
 void lulesh_b200_halo_plan_destroy(lulesh_b200_halo_plan *plan);
 
-/* Host-only self check of the tables behind the experimental warp-brick force kernel
- * (LULESH_B200_BRICK=1; the default K1 is unaffected): the elements are cut into compact
- * groups of <= 32, each group's distinct nodes get local slots, and the corner forces
- * (lulesh.cc:543-546) are pre-added per group node in ascending element order before K2
- * gathers them (lulesh.cc:565-582).  Returns 0 if every (element, corner) contributes
- * exactly once to the right node and the gather table is consistent. */
-int lulesh_b200_brick_plan_check(const lulesh_b200_host_view *view, int32_t *numBricks,
-                                 int32_t *maxNodesPerBrick);
-
 /* "none" (1 rank), "p2p" (NVLink peer stores + flags) or "nccl" (send/recv fallback;
  * forced with LULESH_B200_HALO=nccl). */
 const char *lulesh_b200_halo_mode(lulesh_b200 *h);

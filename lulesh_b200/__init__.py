@@ -90,7 +90,6 @@ ABI_SYMBOLS = (
     "lulesh_b200_kernel_kinematics lulesh_b200_kernel_material lulesh_b200_time_cycles "
     "lulesh_b200_device_bytes lulesh_b200_upload_bytes lulesh_b200_last_error lulesh_b200_halo_mode "
     "lulesh_b200_halo_plan_create lulesh_b200_halo_plan_query lulesh_b200_halo_plan_destroy "
-    "lulesh_b200_brick_plan_check "
     "lulesh_b200_destroy "
     "lulesh_host_domain_new lulesh_host_domain_free lulesh_host_domain_view "
     "lulesh_host_domain_field lulesh_host_domain_ints lulesh_host_domain_scalars "
@@ -130,7 +129,6 @@ _sig("lulesh_b200_destroy", None, _vp)
 _sig("lulesh_b200_halo_plan_create", C.c_int, C.POINTER(HostView), C.POINTER(_vp))
 _sig("lulesh_b200_halo_plan_query", C.c_int, _vp, C.c_char_p, C.POINTER(_pi), C.POINTER(C.c_size_t))
 _sig("lulesh_b200_halo_plan_destroy", None, _vp)
-_sig("lulesh_b200_brick_plan_check", C.c_int, C.POINTER(HostView), C.POINTER(C.c_int32), C.POINTER(C.c_int32))
 _sig("lulesh_host_domain_new", _vp, *([C.c_int] * 11))
 _sig("lulesh_host_domain_free", None, _vp)
 _sig("lulesh_host_domain_view", None, _vp, C.POINTER(HostView))
@@ -224,15 +222,6 @@ class Domain:
 
 HALO_ARRAYS = ("bnode bsum_start bsum_src pack_idx msg_rank msg_count msg_send_off msg_recv_off "
                "mq_idx face_rank face_count face_send_off face_ghost_off").split()
-
-
-def brick_plan_check(domain: Domain):
-    """(numBricks, maxNodesPerBrick) of the warp-brick tables for this Domain; raises if inconsistent."""
-    nb, mx = C.c_int32(), C.c_int32()
-    rc = _lib.lulesh_b200_brick_plan_check(C.byref(domain.refresh_view()), C.byref(nb), C.byref(mx))
-    if rc:
-        raise LuleshError(rc, "brick_plan_check")
-    return nb.value, mx.value
 
 
 def halo_plan(domain: Domain) -> dict:

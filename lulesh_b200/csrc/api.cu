@@ -165,7 +165,6 @@ struct lulesh_b200 {
    std::string halo_mode = "none";
    int launches_per_cycle = 5;
    int k1_grid = 0, k3_grid = 0;   // persistent grids: SMs x resident blocks (capped by the work)
-   bool brick = false;             // experimental: K1 is k_force_brick, K2 gathers brick partials
 };
 
 template <typename T>
@@ -275,121 +274,6 @@ extern "C" int lulesh_b200_get_unique_id(void *out_id)
 
 static int build_comm(lulesh_b200 *h, const lulesh_b200_host_view *v, const void *unique_id,
                       std::vector<unsigned char> &nodeFlags);
-
-// --------------------------------------------------------------------------
-// Warp bricks of the experimental force kernel (k_force_brick, LULESH_B200_BRICK=1).
-// The elements are cut into compact groups of <= 32 (4x4x2 tiles of the brick the view
-// describes; any partition into groups of 32 is correct, compact ones have few distinct
-// nodes).  Everything else is derived from `nodelist` as it is in memory: the distinct nodes
-// of a group (ascending id -> local slot), the 8 slots of every element, and for every
-// local node its contributions (lane, corner) in ascending element order.  `ell` is K2's
-// gather table for this layout: per node the partial sums (brick*BRICK_NODES + slot) that
-// carry it, in ascending brick order.
-// --------------------------------------------------------------------------
-struct BrickPlan {
-   int numBricks = 0, maxNodes = 0;
-   std::vector<int> elem, node;                   // [numBricks][32], [numBricks][BRICK_NODES]
-   std::vector<unsigned long long> slots, sum;    // [numBricks][32], [numBricks][BRICK_NODES]
-   std::vector<int> ell;                          // [8][nn_pad]
-};
-
-static bool build_brick_plan(int sx, int sy, int sz, int ne, int nn, int nn_pad, const int32_t *nodelist,
-                             BrickPlan &pl)
-{
-   const int tx = 4, ty = 4, tz = 2;
-   const int bx = (sx + tx - 1) / tx, by = (sy + ty - 1) / ty, bz = (sz + tz - 1) / tz;
-   if ((long long)bx * by * bz * BRICK_NODES > INT_MAX || (long long)sx * sy * sz != ne) return false;
-   pl.numBricks = bx * by * bz;
-   pl.elem.assign((size_t)pl.numBricks * 32, -1);
-   pl.node.assign((size_t)pl.numBricks * BRICK_NODES, -1);
-   pl.slots.assign((size_t)pl.numBricks * 32, ~0ull);
-   pl.sum.assign((size_t)pl.numBricks * BRICK_NODES, 0ull);
-   pl.ell.assign((size_t)8 * nn_pad, -1);
-   std::vector<int> ell_fill(nn, 0);
-   std::vector<int> local;   // distinct nodes of the brick, ascending
-   for (int b = 0; b < pl.numBricks; ++b) {
-      const int i0 = (b % bx) * tx, j0 = ((b / bx) % by) * ty, k0 = (b / (bx * by)) * tz;
-      int *el = &pl.elem[(size_t)b * 32];
-      int cnt = 0;
-      for (int k = k0; k < std::min(k0 + tz, sz); ++k)       // ascending element id
-         for (int j = j0; j < std::min(j0 + ty, sy); ++j)
-            for (int i = i0; i < std::min(i0 + tx, sx); ++i) el[cnt++] = (k * sy + j) * sx + i;
-      local.clear();
-      for (int l = 0; l < cnt; ++l)
-         for (int c = 0; c < 8; ++c) local.push_back(nodelist[(size_t)8 * el[l] + c]);
-      std::sort(local.begin(), local.end());
-      local.erase(std::unique(local.begin(), local.end()), local.end());
-      if ((int)local.size() > BRICK_NODES) return false;   // not compact enough: the caller keeps k_force
-      pl.maxNodes = std::max(pl.maxNodes, (int)local.size());
-      int ncontrib[BRICK_NODES] = {0};
-      for (int l = 0; l < cnt; ++l) {
-         unsigned long long sl = 0;
-         for (int c = 0; c < 8; ++c) {
-            const int n = nodelist[(size_t)8 * el[l] + c];
-            const int slot = (int)(std::lower_bound(local.begin(), local.end(), n) - local.begin());
-            sl |= (unsigned long long)slot << (8 * c);
-            if (ncontrib[slot] >= 8) return false;          // more than 8 corners at a node
-            pl.sum[(size_t)b * BRICK_NODES + slot] |= (unsigned long long)(l * 8 + c) << (8 * ncontrib[slot]);
-            ++ncontrib[slot];
-         }
-         pl.slots[(size_t)b * 32 + l] = sl;
-      }
-      for (int s = 0; s < (int)local.size(); ++s) {
-         const int n = local[s];
-         pl.node[(size_t)b * BRICK_NODES + s] = n | ((ncontrib[s] - 1) << 28);   // 1..8 contributions in bits 28-30
-         if (ell_fill[n] >= 8) return false;                 // a node in more than 8 bricks
-         pl.ell[(size_t)ell_fill[n]++ * nn_pad + n] = b * BRICK_NODES + s;   // ascending brick order
-      }
-   }
-   return true;
-}
-
-// Host-only self check of the plan (tests/test_host_domain.py): every (element, corner) is
-// one contribution of exactly one brick node, that node is the element's node, and K2's table
-// lists every brick partial of a node once.  Returns 0, or -1 with the reason in last_error.
-extern "C" int lulesh_b200_brick_plan_check(const lulesh_b200_host_view *v, int32_t *numBricks, int32_t *maxNodes)
-{
-   if (!v || !v->nodelist || v->numElem <= 0 || v->numNode <= 0) return fail(LULESH_B200_EINVAL, "bad view");
-   const int ne = v->numElem, nn = v->numNode, nn_pad = (nn + 31) & ~31;
-   BrickPlan pl;
-   if (!build_brick_plan(v->sizeX, v->sizeY, v->sizeZ, ne, nn, nn_pad, v->nodelist, pl))
-      return fail(LULESH_B200_EINVAL, "mesh does not tile into bricks of <= %d nodes", BRICK_NODES);
-   std::vector<char> seen((size_t)8 * ne, 0);
-   std::vector<int> refs(nn, 0);
-   for (int b = 0; b < pl.numBricks; ++b)
-      for (int s = 0; s < BRICK_NODES; ++s) {
-         const int w = pl.node[(size_t)b * BRICK_NODES + s];
-         if (w < 0) continue;
-         const int n = w & 0x0fffffff, cnt = (w >> 28) + 1;
-         ++refs[n];
-         int last = -1;
-         for (int t = 0; t < cnt; ++t) {
-            const int code = (int)((pl.sum[(size_t)b * BRICK_NODES + s] >> (8 * t)) & 0xff);
-            const int l = code >> 3, c = code & 7, e = pl.elem[(size_t)b * 32 + l];
-            if (e < 0 || v->nodelist[(size_t)8 * e + c] != n) return fail(LULESH_B200_EINVAL, "contribution of brick %d names the wrong node", b);
-            if (((pl.slots[(size_t)b * 32 + l] >> (8 * c)) & 0xff) != (unsigned)s) return fail(LULESH_B200_EINVAL, "slot table of brick %d disagrees", b);
-            if (t > 0 && e <= last) return fail(LULESH_B200_EINVAL, "contributions of brick %d are not in element order", b);
-            last = e;
-            if (seen[(size_t)8 * e + c]++) return fail(LULESH_B200_EINVAL, "corner (%d,%d) contributes twice", e, c);
-         }
-      }
-   for (size_t i = 0; i < seen.size(); ++i)
-      if (!seen[i]) return fail(LULESH_B200_EINVAL, "corner %zu contributes nowhere", i);
-   for (int n = 0; n < nn; ++n) {
-      int k = 0, last = -1;
-      for (int m = 0; m < 8; ++m) {
-         const int r = pl.ell[(size_t)m * nn_pad + n];
-         if (r < 0) continue;
-         if (r <= last || (pl.node[r] & 0x0fffffff) != n) return fail(LULESH_B200_EINVAL, "gather table entry of node %d is wrong", n);
-         last = r;
-         ++k;
-      }
-      if (k != refs[n]) return fail(LULESH_B200_EINVAL, "node %d: %d brick partials, %d table entries", n, refs[n], k);
-   }
-   if (numBricks) *numBricks = pl.numBricks;
-   if (maxNodes) *maxNodes = pl.maxNodes;
-   return 0;
-}
 
 // Everything create() can check without a GPU.  The kernels index with the connectivity,
 // neighbour, corner and region arrays unchecked, so anything out of range is rejected here.
@@ -558,10 +442,7 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
       UP_INT(lzetam, ne) UP_INT(lzetap, ne) UP_INT(elemBC, ne)
 #undef UP_INT
    }
-   P.fstride = (size_t)8 * P.ne_pad;
-   const char *brick_env = getenv("LULESH_B200_BRICK");
-   const bool want_brick = brick_env && brick_env[0] == '1';
-   if (!want_brick && (rc = dev_zero(h, &P.fcorner, (size_t)24 * P.ne_pad))) return rc;
+   if ((rc = dev_zero(h, &P.fcorner, (size_t)24 * P.ne_pad))) return rc;
 
    std::vector<unsigned char> nodeFlags(nn, 0);
    unsigned char *d_nodeFlags = nullptr;
@@ -687,35 +568,6 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
       if ((rc = dev_upload(h, &p_, nodeFlags.data(), nodeFlags.size()))) return rc;
       P.nodeFlags = p_;
    }
-   if (want_brick) {
-      // experimental warp-brick force kernel: needs the connectivity on the host
-      std::vector<int32_t> nl_host;
-      const int32_t *nl = v->nodelist;
-      if (gen) {
-         nl_host.resize((size_t)8 * ne);
-         CK(cudaMemcpy(nl_host.data(), P.nodelist, nl_host.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-         nl = nl_host.data();
-      }
-      BrickPlan pl;
-      if (!build_brick_plan(v->sizeX, v->sizeY, v->sizeZ, ne, nn, P.nn_pad, nl, pl))
-         return fail(LULESH_B200_EINVAL, "LULESH_B200_BRICK=1: the mesh does not tile into bricks of <= %d nodes", BRICK_NODES);
-      int *pi_;
-      unsigned long long *pu_;
-      if ((rc = dev_upload(h, &pi_, pl.elem.data(), pl.elem.size()))) return rc;
-      P.brickElem = pi_;
-      if ((rc = dev_upload(h, &pi_, pl.node.data(), pl.node.size()))) return rc;
-      P.brickNode = pi_;
-      if ((rc = dev_upload(h, &pu_, pl.slots.data(), pl.slots.size()))) return rc;
-      P.brickSlots = pu_;
-      if ((rc = dev_upload(h, &pu_, pl.sum.data(), pl.sum.size()))) return rc;
-      P.brickSum = pu_;
-      if ((rc = dev_upload(h, &pi_, pl.ell.data(), pl.ell.size()))) return rc;
-      P.cornerEll = pi_;          // K2 and the boundary gather now read brick partials
-      P.numBricks = pl.numBricks;
-      P.fstride = (size_t)pl.numBricks * BRICK_NODES;
-      if ((rc = dev_zero(h, &P.fcorner, 3 * P.fstride))) return rc;
-      h->brick = true;
-   }
    {  // persistent grids for the cp.async-pipelined element kernels
       int occ1 = 0, occ3 = 0;
       CK(cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
@@ -726,14 +578,6 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_kinematics, K3_THREADS, K3_SMEM_BYTES));
       if (occ1 < 1 || occ3 < 1) return fail(LULESH_B200_ECUDA, "element kernels do not fit on an SM");
       h->k1_grid = std::min(blocks_for(ne, K1_THREADS), prop.multiProcessorCount * occ1);
-      if (h->brick) {
-         int occb = 0;
-         CK(cudaFuncSetAttribute(k_force_brick, cudaFuncAttributeMaxDynamicSharedMemorySize, K1B_SMEM_BYTES));
-         CK(cudaFuncSetAttribute(k_force_brick, cudaFuncAttributePreferredSharedMemoryCarveout, 75));
-         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, k_force_brick, K1_THREADS, K1B_SMEM_BYTES));
-         if (occb < 1) return fail(LULESH_B200_ECUDA, "k_force_brick does not fit on an SM");
-         h->k1_grid = std::min(blocks_for(P.numBricks, K1_THREADS / 32), prop.multiProcessorCount * occb);
-      }
       h->k3_grid = std::min(blocks_for(ne, K3_THREADS), prop.multiProcessorCount * occ3);
    }
    CK(cudaDeviceSynchronize());
@@ -1207,8 +1051,7 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
       h->launches += 2;
    }
    if (marks) CK(cudaEventRecord(marks[1], s));
-   if (h->brick) k_force_brick<<<h->k1_grid, K1_THREADS, K1B_SMEM_BYTES, s>>>(P);
-   else k_force<<<h->k1_grid, K1_THREADS, K1_SMEM_BYTES, s>>>(P);
+   k_force<<<h->k1_grid, K1_THREADS, K1_SMEM_BYTES, s>>>(P);
    if (marks) CK(cudaEventRecord(marks[2], s));
    if (h->numRanks > 1 && h->p2p) {
       // Shared nodes: gather own partials -> store them into the neighbours -> wait for theirs ->
@@ -1506,8 +1349,7 @@ extern "C" int lulesh_b200_kernel_force(lulesh_b200 *h)
 {
    if (!h) return fail(LULESH_B200_EINVAL, "null handle");
    CK(cudaSetDevice(h->device));
-   if (h->brick) k_force_brick<<<h->k1_grid, K1_THREADS, K1B_SMEM_BYTES, h->stream>>>(h->P);
-   else k_force<<<h->k1_grid, K1_THREADS, K1_SMEM_BYTES, h->stream>>>(h->P);
+   k_force<<<h->k1_grid, K1_THREADS, K1_SMEM_BYTES, h->stream>>>(h->P);
    return finish_kernel(h);
 }
 

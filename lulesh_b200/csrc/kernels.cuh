@@ -75,13 +75,6 @@ struct KParams {
    int fhalo_stride;
    const struct PeerCounters *peer_cnt;   // non-null in peer-to-peer mode: fhalo is double-buffered by sequence parity
    int unit_rho0;                 // refdens == 1.0: EOS skips the exact no-op division
-   size_t fstride;                // distance between the three axis planes of the force buffer K2 gathers from
-   // warp-brick force kernel (experimental, LULESH_B200_BRICK=1): see k_force_brick
-   int numBricks;
-   const int *brickElem;          // [numBricks][32] element of each lane, -1 = none
-   const int *brickNode;          // [numBricks][BRICK_NODES] node id | (contributions - 1) << 28, -1 = unused slot
-   const unsigned long long *brickSlots;   // [numBricks][32] the 8 local node slots of the lane's element, one byte each
-   const unsigned long long *brickSum;     // [numBricks][BRICK_NODES] contribution codes (lane*8 + corner), one byte each
    lulesh_b200_constants c;
 };
 
@@ -103,17 +96,11 @@ constexpr int K2_THREADS = 256;
 constexpr int K3_THREADS = LB_K3_THREADS;
 constexpr int K3_BLOCKS_PER_SM = LB_K3_BPS;
 constexpr int K1_SMEM_BYTES = 54 * K1_THREADS * 8;   // cp.async staging tile: 48 node values + 6 scalars
-// warp-brick force kernel: per warp  node values [2][6][BRICK_NODES], element scalars [2][6][32],
-// corner forces [24][32], contribution codes [2][BRICK_NODES] (u64), node words [2][BRICK_NODES] (i32)
-constexpr int BRICK_NODES = 96;
-constexpr int K1B_WARP_BYTES = 2 * 6 * BRICK_NODES * 8 + 2 * 6 * 32 * 8 + 24 * 32 * 8 + 2 * BRICK_NODES * 8 + 2 * BRICK_NODES * 4;
-constexpr int K1B_SMEM_BYTES = (K1_THREADS / 32) * K1B_WARP_BYTES;
 constexpr int K3_SMEM_BYTES = 50 * K3_THREADS * 8;   // 48 node values + volo, v
 constexpr int MAT_THREADS = 128;
 
 __global__ void k_time_increment(Ctl *ctl, int phase);
 __global__ void k_force(const KParams P);
-__global__ void k_force_brick(const KParams P);
 __global__ void k_node(const KParams P, int storeDebug);
 __global__ void k_node_boundary_gather(const KParams P);
 __global__ void k_node_boundary_update(const KParams P, int storeDebug);

@@ -225,22 +225,6 @@ def test_create_rejects_region_lists_that_are_not_a_partition(lb):
     assert not h.value
 
 
-@pytest.mark.parametrize("sizes,expect", [((8, 8, 8), (16, 75)), ((5, 7, 3), (8, 75)), ((1, 1, 1), (1, 8)),
-                                          ((13, 4, 2), (4, 75)), ((4, 4, 2), (1, 75))])
-def test_brick_plan_is_a_partition_of_the_corner_forces(lb, sizes, expect):
-    """Tables of the experimental warp-brick force kernel: every (element, corner) contributes
-    exactly once, to the right node, in element order; K2's table lists every partial once."""
-    d = lb.Domain(sizes[0], sizes=sizes)
-    assert lb.brick_plan_check(d) == expect
-    nl = d.ints("nodelist")
-    saved = nl.copy()
-    nl[:] = np.random.default_rng(7).integers(0, d.numNode, nl.size)   # bricks with > 96 distinct nodes do not fit
-    if d.numElem >= 32 and d.numNode > 150:
-        with pytest.raises(lb.LuleshError):
-            lb.brick_plan_check(d)
-    nl[:] = saved
-
-
 def read_vtk(path):
     """Minimal reader of the binary legacy-VTK files written by vizdump.cc."""
     raw = open(path, "rb").read()
