@@ -21,7 +21,8 @@ def all_plans(lb, decomp, sizes):
 
 
 @pytest.mark.parametrize("decomp,sizes", [((1, 1, 2), (4, 4, 2)), ((1, 2, 2), (4, 3, 2)),
-                                          ((2, 2, 2), (3, 3, 3)), ((3, 3, 3), (2, 2, 2))])
+                                          ((2, 2, 2), (3, 3, 3)), ((3, 3, 3), (2, 2, 2)),
+                                          ((2, 1, 3), (2, 5, 3)), ((1, 3, 2), (1, 1, 1)), ((2, 2, 2), (1, 2, 1))])
 def test_halo_plan_is_pairwise_consistent(lb, decomp, sizes):
     doms, plans = all_plans(lb, decomp, sizes)
     for r, (d, p) in enumerate(zip(doms, plans)):
