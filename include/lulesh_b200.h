@@ -174,7 +174,13 @@ int lulesh_b200_sum_nodal_mass(lulesh_b200 *h);
  * cycles are enqueued between host polls of the control block (cycles issued
  * after termination are device-side no-ops).  `cb` (may be NULL) forces a
  * per-cycle poll, like -p.  Returns 0 / -1 / -2 as the reference's exit
- * codes (lulesh.h:42). */
+ * codes (lulesh.h:42).
+ * Several ranks: the ranks of one communicator advance in lockstep (every cycle
+ * contains exchanges that all of them take part in), so EVERY rank must call
+ * this with the same `max_cycles` and the same `sync_every`; a rank with a
+ * callback polls every cycle, so when any rank passes `cb` the others pass
+ * sync_every = 1.  A device error on one rank (-1 / -2) reaches all ranks with
+ * the next dt reduction, and every rank returns it from the same cycle. */
 int lulesh_b200_run(lulesh_b200 *h, int32_t max_cycles, int32_t sync_every,
                     lulesh_b200_progress_cb cb, void *user);
 

@@ -287,7 +287,10 @@ static int validate_view(const lulesh_b200_host_view *v, bool generated)
       return fail(LULESH_B200_EINVAL, "inconsistent sizes in host view");
    if ((long long)ne + 15 > INT_MAX / 8 || (long long)nn + 31 > INT_MAX / 8)
       return fail(LULESH_B200_EINVAL, "brick too large for int32 indices");
-   if (v->numRanks < 1 || v->px * v->py * v->pz != v->numRanks || v->rank < 0 || v->rank >= v->numRanks)
+   if (v->numRanks < 1 || v->px < 1 || v->py < 1 || v->pz < 1 || v->px * v->py * v->pz != v->numRanks ||
+       v->rank < 0 || v->rank >= v->numRanks || v->colLoc < 0 || v->colLoc >= v->px || v->rowLoc < 0 ||
+       v->rowLoc >= v->py || v->planeLoc < 0 || v->planeLoc >= v->pz ||
+       v->rank != v->planeLoc * v->px * v->py + v->rowLoc * v->px + v->colLoc)   // lulesh-init.cc:732-734
       return fail(LULESH_B200_EINVAL, "inconsistent decomposition in host view");
    if (!v->regElemSize || !v->regElemlist || v->numReg < 1 ||
        (!generated && (!v->x || !v->y || !v->z || !v->xd || !v->yd || !v->zd || !v->nodalMass || !v->nodelist ||
@@ -568,17 +571,32 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
       if ((rc = dev_upload(h, &p_, nodeFlags.data(), nodeFlags.size()))) return rc;
       P.nodeFlags = p_;
    }
-   {  // persistent grids for the cp.async-pipelined element kernels
-      int occ1 = 0, occ3 = 0;
+   {  // persistent grids for the cp.async-pipelined element kernels: SMs x resident blocks.
+      // The shared-memory carveout is the smallest one that still reaches the residency the
+      // register file allows, so that as much as possible of the SM's 256 KB stays L1 for
+      // the node gathers.
       CK(cudaFuncSetAttribute(k_force, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
       CK(cudaFuncSetAttribute(k_kinematics, cudaFuncAttributeMaxDynamicSharedMemorySize, K3_SMEM_BYTES));
-      CK(cudaFuncSetAttribute(k_force, cudaFuncAttributePreferredSharedMemoryCarveout, 75));
-      CK(cudaFuncSetAttribute(k_kinematics, cudaFuncAttributePreferredSharedMemoryCarveout, 75));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_force, K1_THREADS, K1_SMEM_BYTES));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, k_kinematics, K3_THREADS, K3_SMEM_BYTES));
+      auto residency = [&](auto kernel, int threads, int smem, int *occ_out) -> int {
+         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+         int occ = 0;
+         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
+         const double need = (double)occ * (smem + 1024);   // 1 KB per block is reserved by the system
+         int pct = (int)(100.0 * need / (double)prop.sharedMemPerMultiprocessor) + 1;
+         pct = std::max(25, std::min(100, pct));
+         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+         *occ_out = occ;
+         return 0;
+      };
+      int occ1 = 0, occ3 = 0;
+      if ((rc = residency(k_force, K1_THREADS, K1_SMEM_BYTES, &occ1))) return rc;
+      if ((rc = residency(k_kinematics, K3_THREADS, K3_SMEM_BYTES, &occ3))) return rc;
       if (occ1 < 1 || occ3 < 1) return fail(LULESH_B200_ECUDA, "element kernels do not fit on an SM");
       h->k1_grid = std::min(blocks_for(ne, K1_THREADS), prop.multiProcessorCount * occ1);
       h->k3_grid = std::min(blocks_for(ne, K3_THREADS), prop.multiProcessorCount * occ3);
+      if (getenv("LULESH_B200_VERBOSE"))
+         fprintf(stderr, "lulesh_b200: K1 %d x %d threads/SM, K3 %d x %d threads/SM\n", occ1, K1_THREADS, occ3,
+                 K3_THREADS);
    }
    CK(cudaDeviceSynchronize());
    return 0;
@@ -1160,9 +1178,18 @@ static int fetch_ctl(lulesh_b200 *h)
    return 0;
 }
 
+// New cycle limit for the device-side loop condition (lulesh.cc:2745).  `skip_force` is that
+// condition evaluated one cycle ahead (see k_time_increment), so it is re-derived here from the
+// current time and cycle.
 static int set_max_cycles(lulesh_b200 *h, int max_cycles)
 {
-   CK(cudaMemcpyAsync(&h->P.ctl->max_cycles, &max_cycles, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+   int rc;
+   if ((rc = fetch_ctl(h))) return rc;
+   const Ctl &c = *h->h_ctl;
+   const int v[2] = {max_cycles, (c.time < c.stoptime && c.cycle < max_cycles) ? 0 : 1};
+   CK(cudaMemcpyAsync(&h->P.ctl->max_cycles, &v[0], sizeof(int), cudaMemcpyHostToDevice, h->stream));
+   CK(cudaMemcpyAsync(&h->P.ctl->skip_force, &v[1], sizeof(int), cudaMemcpyHostToDevice, h->stream));
+   CK(cudaStreamSynchronize(h->stream));   // v[] is a stack array
    return 0;
 }
 
@@ -1287,6 +1314,7 @@ extern "C" int lulesh_b200_set_scalars(lulesh_b200 *h, const lulesh_b200_scalars
    c.deltatimemultlb = in->deltatimemultlb; c.deltatimemultub = in->deltatimemultub;
    c.dtmax = in->dtmax; c.stoptime = in->stoptime; c.cycle = in->cycle; c.error = in->error;
    c.done = 0;
+   c.skip_force = (c.time < c.stoptime && c.cycle < c.max_cycles) ? 0 : 1;
    CK(cudaMemcpy(h->P.ctl, &c, sizeof c, cudaMemcpyHostToDevice));
    return 0;
 }

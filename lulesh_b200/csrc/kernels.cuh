@@ -41,7 +41,8 @@ struct Ctl {
    double gnewdt;        // this rank's candidate, input/output of the min-allreduce
    int cycle, max_cycles;
    int done;             // 1: time >= stoptime or cycle >= max_cycles -> kernels no-op
-   int error;            // sticky: 0 / VolumeError -1 / QStopError -2
+   int error;            // sticky, first one wins: 0 / VolumeError -1 / QStopError -2 / infrastructure
+   int skip_force;       // `done` of the NEXT cycle, for the kernels that run next to its dt chain
 };
 
 struct KParams {
