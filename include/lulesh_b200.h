@@ -225,11 +225,34 @@ int lulesh_b200_kernel_material(lulesh_b200 *h);
  * test against stoptime beyond the device-side one) bracketed by CUDA events
  * on the handle's stream and returns the elapsed milliseconds; when
  * `per_kernel_ms` != NULL it receives LULESH_B200_NUM_KERNELS accumulated
- * per-kernel event times (this mode launches kernels individually, without
- * the CUDA graph). */
+ * main-stream intervals K6 | K1 | K2 | K3 | K45 (this mode launches the kernels
+ * eagerly instead of replaying the CUDA graph; streams and overlap are the
+ * same; at several ranks an interval includes the time its kernel's stream
+ * waited for the exchange it depends on, see lulesh_b200_timeline). */
 #define LULESH_B200_NUM_KERNELS 5
 int lulesh_b200_time_cycles(lulesh_b200 *h, int32_t cycles, float *total_ms,
                             float *per_kernel_ms, int64_t *launches);
+
+/* Per-cycle timeline (milliseconds, averaged over `cycles` cycles launched exactly like the
+ * cycles of lulesh_b200_run: same streams, same overlap).  Main-stream intervals first; at
+ * several ranks the three chains that run on the communication stream underneath them follow
+ * (zero at one rank).  "join wait" = time the main stream sat waiting for the comm stream. */
+enum lulesh_b200_timeline_slot {
+   LULESH_TL_TIME_INCREMENT = 0,  /* K6 on the main stream (one rank only)              */
+   LULESH_TL_K1,                  /* force kernel                                       */
+   LULESH_TL_K2,                  /* node kernel (interior nodes at several ranks)      */
+   LULESH_TL_NODE_JOIN_WAIT,      /* main stream waiting for the shared-node chain      */
+   LULESH_TL_K3,                  /* kinematics + monotonic-Q gradients                 */
+   LULESH_TL_K45_INTERIOR,        /* material kernel over elements without ghost reads  */
+   LULESH_TL_MONOQ_JOIN_WAIT,     /* main stream waiting for the MonoQ exchange         */
+   LULESH_TL_K45_TAIL,            /* material kernel over the remaining elements        */
+   LULESH_TL_CYCLE,               /* whole cycle, main stream                           */
+   LULESH_TL_COMM_DT,             /* comm stream: dt candidate, min over ranks, K6      */
+   LULESH_TL_COMM_NODE,           /* comm stream: shared-node gather, exchange, update  */
+   LULESH_TL_COMM_MONOQ,          /* comm stream: MonoQ pack, exchange                  */
+   LULESH_B200_TIMELINE_N
+};
+int lulesh_b200_timeline(lulesh_b200 *h, int32_t cycles, float *out_ms /* [LULESH_B200_TIMELINE_N] */);
 
 /* Bytes resident in HBM for this handle / bytes uploaded by create. */
 size_t lulesh_b200_device_bytes(lulesh_b200 *h);

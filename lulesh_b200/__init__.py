@@ -32,6 +32,9 @@ ABI_VERSION = 1
 UNIQUE_ID_BYTES = 128
 NUM_KERNELS = 5
 KERNEL_NAMES = ("time_increment", "force_elem", "node_update", "kinematics_grad", "material")
+# slots of lulesh_b200_timeline (enum lulesh_b200_timeline_slot)
+TIMELINE_NAMES = ("time_increment", "k1_force", "k2_node", "node_join_wait", "k3_kinematics", "k45_interior",
+                  "monoq_join_wait", "k45_tail", "cycle", "comm_dt", "comm_node", "comm_monoq")
 
 # status codes (lulesh.h:42 + infrastructure)
 OK, VOLUME_ERROR, QSTOP_ERROR, EINVAL, ECUDA, ENCCL = 0, -1, -2, -10, -11, -12
@@ -87,7 +90,7 @@ ABI_SYMBOLS = (
     "lulesh_b200_step lulesh_b200_get_scalars lulesh_b200_set_scalars lulesh_b200_download "
     "lulesh_b200_upload lulesh_b200_field_count lulesh_b200_set_debug "
     "lulesh_b200_kernel_time_increment lulesh_b200_kernel_force lulesh_b200_kernel_node "
-    "lulesh_b200_kernel_kinematics lulesh_b200_kernel_material lulesh_b200_time_cycles "
+    "lulesh_b200_kernel_kinematics lulesh_b200_kernel_material lulesh_b200_time_cycles lulesh_b200_timeline "
     "lulesh_b200_device_bytes lulesh_b200_upload_bytes lulesh_b200_last_error lulesh_b200_halo_mode "
     "lulesh_b200_halo_plan_create lulesh_b200_halo_plan_query lulesh_b200_halo_plan_destroy "
     "lulesh_b200_destroy "
@@ -121,6 +124,7 @@ for _k in ("time_increment", "force", "kinematics", "material"):
 _sig("lulesh_b200_kernel_node", C.c_int, _vp, C.c_int)
 _sig("lulesh_b200_time_cycles", C.c_int, _vp, C.c_int32, C.POINTER(C.c_float),
      C.POINTER(C.c_float), C.POINTER(C.c_int64))
+_sig("lulesh_b200_timeline", C.c_int, _vp, C.c_int32, C.POINTER(C.c_float))
 _sig("lulesh_b200_device_bytes", C.c_size_t, _vp)
 _sig("lulesh_b200_upload_bytes", C.c_size_t, _vp)
 _sig("lulesh_b200_last_error", C.c_char_p)
@@ -327,6 +331,12 @@ class Device:
         rc = _lib.lulesh_b200_time_cycles(self._h, cycles, C.byref(total), pk, C.byref(launches))
         self._check(rc, "time_cycles")
         return total.value, (list(pk) if per_kernel else None), launches.value
+
+    def timeline(self, cycles):
+        """Per-cycle timeline in ms (dict), measured on the shipped two-stream schedule."""
+        out = (C.c_float * len(TIMELINE_NAMES))()
+        self._check(_lib.lulesh_b200_timeline(self._h, cycles, out), "timeline")
+        return dict(zip(TIMELINE_NAMES, (float(v) for v in out)))
 
     halo_mode = property(lambda s: _lib.lulesh_b200_halo_mode(s._h).decode())
     device_bytes = property(lambda s: _lib.lulesh_b200_device_bytes(s._h))

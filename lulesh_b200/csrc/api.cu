@@ -163,6 +163,7 @@ struct lulesh_b200 {
    DtSlot **d_peer_slots = nullptr;
    std::vector<void *> ipc_opened;
    std::string halo_mode = "none";
+   bool nccl_warm = false;
    int launches_per_cycle = 5;
    int k1_grid = 0, k3_grid = 0;   // persistent grids: SMs x resident blocks (capped by the work)
 };
@@ -363,7 +364,11 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    h->numRanks = v->numRanks;
    h->rank = v->rank;
    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-   CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+   {  // the exchange kernels are tiny and latency-critical: their blocks go first when an SM frees up
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
+   }
    CK(cudaEventCreateWithFlags(&h->ev_a, cudaEventDisableTiming));
    CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -497,16 +502,28 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
    // bound by their three dependent gathers; interleaving them lets each SM overlap the
    // two, and the expensive blocks are all issued within the first ~3/4 of the grid so
    // that they never form the tail.
+   // Several ranks: the elements that read ghost values of delv_* (a *_COMM face,
+   // lulesh.cc:1782-1783) form a second list at the tail, launched separately once the
+   // MonoQ exchange has landed; everything else starts right behind K3 and hides the exchange.
    {
       struct Block { int first, rep; };
       std::vector<int> entries;
-      std::vector<Block> heavy, light;
+      std::vector<Block> heavy, light, face;
       long long total = 0;
       int max_rep = 0, min_rep = INT_MAX;
       for (int r = 0; r < v->numReg; ++r) {
          const int rep = region_rep(r, v->numReg, v->cost);
          if (v->regElemSize[r] > 0) { max_rep = std::max(max_rep, rep); min_rep = std::min(min_rep, rep); }
       }
+      const int sx = v->sizeX, sy = v->sizeY, sz = v->sizeZ;
+      auto reads_ghosts = [&](int el) -> bool {
+         if (v->numRanks == 1) return false;
+         if (!gen) return (v->elemBC[el] & (XI_M_COMM | XI_P_COMM | ETA_M_COMM | ETA_P_COMM | ZETA_M_COMM | ZETA_P_COMM)) != 0;
+         const int i = el % sx, j = (el / sx) % sy, k = el / (sx * sy);   // the generated brick (setup.cu)
+         return (i == 0 && v->colLoc > 0) || (i == sx - 1 && v->colLoc < v->px - 1) ||
+                (j == 0 && v->rowLoc > 0) || (j == sy - 1 && v->rowLoc < v->py - 1) ||
+                (k == 0 && v->planeLoc > 0) || (k == sz - 1 && v->planeLoc < v->pz - 1);
+      };
       // Regions with the same repetition count are one cost class: every element is the same
       // material, only `rep` differs (lulesh.cc:2393-2400).  The lists of a class are merged
       // and sorted by element id, which lengthens the contiguous runs a warp sees (the
@@ -518,7 +535,7 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
       }
       std::sort(classes.begin(), classes.end(), std::greater<int>());
       for (int rep : classes) {
-         std::vector<int> merged;
+         std::vector<int> merged[2];   // [0] interior, [1] elements reading ghost slots
          for (int r = 0; r < v->numReg; ++r) {
             if (region_rep(r, v->numReg, v->cost) != rep) continue;
             const int n = v->regElemSize[r];
@@ -526,15 +543,17 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
             for (int t = 0; t < n; ++t) {
                const int el = v->regElemlist[r][t];
                if (el < 0 || el >= ne) return fail(LULESH_B200_EINVAL, "region list entry out of range");
-               merged.push_back(el);
+               merged[reads_ghosts(el) ? 1 : 0].push_back(el);
             }
          }
-         std::sort(merged.begin(), merged.end());
-         const int n = (int)merged.size();
-         for (int t0 = 0; t0 < n; t0 += MAT_THREADS) {
-            Block b{(int)entries.size(), rep};
-            for (int t = t0; t < t0 + MAT_THREADS; ++t) entries.push_back(t < n ? merged[t] : -1);
-            ((rep == max_rep && max_rep > min_rep) ? heavy : light).push_back(b);
+         for (int part = 0; part < 2; ++part) {
+            std::sort(merged[part].begin(), merged[part].end());
+            const int n = (int)merged[part].size();
+            for (int t0 = 0; t0 < n; t0 += MAT_THREADS) {
+               Block b{(int)entries.size(), rep};
+               for (int t = t0; t < t0 + MAT_THREADS; ++t) entries.push_back(t < n ? merged[part][t] : -1);
+               (part == 1 ? face : (rep == max_rep && max_rep > min_rep) ? heavy : light).push_back(b);
+            }
          }
       }
       if (total != ne) return fail(LULESH_B200_EINVAL, "region lists cover %lld of %d elements", total, ne);
@@ -546,6 +565,8 @@ static int create_impl(lulesh_b200 *h, const lulesh_b200_host_view *v, int devic
          while (li < upto && li < light.size()) sched.push_back(light[li++]);
       }
       while (li < light.size()) sched.push_back(light[li++]);
+      P.numWorkBlocksInterior = (int)sched.size();
+      sched.insert(sched.end(), face.begin(), face.end());
       std::vector<int> work, reps;
       work.reserve(entries.size());
       for (const Block &b : sched) {
@@ -997,132 +1018,167 @@ extern "C" void lulesh_b200_destroy(lulesh_b200 *h)
 // the cycle
 // --------------------------------------------------------------------------
 
-// node-halo exchange of the three force planes (or the replicated mass)
-static int exchange_nodes(lulesh_b200 *h)
+// NCCL fallback of the node-halo exchange of the three force planes (or the replicated
+// mass), entirely on stream `cs`: pack, one group of send/recv per neighbour.
+static int exchange_nodes(lulesh_b200 *h, cudaStream_t cs)
 {
    const KParams &P = h->P;
-   k_gather_index<<<blocks_for((int)h->send_total, 256), 256, 0, h->stream>>>(
+   k_gather_index<<<blocks_for((int)h->send_total, 256), 256, 0, cs>>>(
       h->sendbuf, P.fhalo, h->pack_idx, (int)h->send_total);
-   CK(cudaEventRecord(h->ev_a, h->stream));
-   CK(cudaStreamWaitEvent(h->comm_stream, h->ev_a, 0));
    NK(h->nccl->GroupStart());
    for (const Message &m : h->msgs) {
-      NK(h->nccl->Recv(P.fhalo + m.recv_off, (size_t)3 * m.count, ncclDouble, m.rank, h->comm, h->comm_stream));
-      NK(h->nccl->Send(h->sendbuf + m.send_off, (size_t)3 * m.count, ncclDouble, m.rank, h->comm, h->comm_stream));
+      NK(h->nccl->Recv(P.fhalo + m.recv_off, (size_t)3 * m.count, ncclDouble, m.rank, h->comm, cs));
+      NK(h->nccl->Send(h->sendbuf + m.send_off, (size_t)3 * m.count, ncclDouble, m.rank, h->comm, cs));
    }
    NK(h->nccl->GroupEnd());
-   CK(cudaEventRecord(h->ev_b, h->comm_stream));
    h->launches += 1;
    return 0;
 }
 
-static int exchange_monoq(lulesh_b200 *h)
+static int exchange_monoq(lulesh_b200 *h, cudaStream_t cs)
 {
    const KParams &P = h->P;
-   k_gather_index<<<blocks_for((int)h->mq_total, 256), 256, 0, h->stream>>>(
+   k_gather_index<<<blocks_for((int)h->mq_total, 256), 256, 0, cs>>>(
       h->mq_send, P.delv_xi, h->mq_idx, (int)h->mq_total);
-   CK(cudaEventRecord(h->ev_a, h->stream));
-   CK(cudaStreamWaitEvent(h->comm_stream, h->ev_a, 0));
    NK(h->nccl->GroupStart());
    for (const FaceMessage &f : h->faces)
       for (int a = 0; a < 3; ++a) {   // receive straight into the ghost slots: zero unpack
          NK(h->nccl->Recv(P.delv_xi + (size_t)a * P.allElem + f.ghost_off, f.count, ncclDouble, f.rank,
-                          h->comm, h->comm_stream));
+                          h->comm, cs));
          NK(h->nccl->Send(h->mq_send + f.send_off + (size_t)a * f.count, f.count, ncclDouble, f.rank,
-                          h->comm, h->comm_stream));
+                          h->comm, cs));
       }
    NK(h->nccl->GroupEnd());
-   CK(cudaEventRecord(h->ev_b, h->comm_stream));
-   CK(cudaStreamWaitEvent(h->stream, h->ev_b, 0));
    h->launches += 1;
    return 0;
 }
 
-// enqueue one TimeIncrement + LagrangeLeapFrog on h->stream (no host sync)
-static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *marks /* 6 or null */)
+// Timeline events of one cycle (lulesh_b200_timeline / per-kernel timing).  M_* are recorded on
+// the main stream, C_* on the comm stream (several ranks only).
+enum {
+   M_START = 0, M_K1_START, M_K1_END, M_K2_END, M_NODE_JOIN, M_K3_END, M_K45I_END, M_MONOQ_JOIN, M_END,
+   C_DT_START, C_DT_END, C_NODE_START, C_NODE_END, C_MQ_START, C_MQ_END, TL_EVENTS
+};
+
+// enqueue one TimeIncrement + LagrangeLeapFrog on h->stream (no host sync).
+// `tl` (TL_EVENTS events or null) receives the timeline; the schedule is the same either way.
+static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *tl)
 {
    const KParams &P = h->P;
-   cudaStream_t s = h->stream;
+   cudaStream_t s = h->stream, cs = h->comm_stream;
    const int dbg = h->debug;
-   if (marks) CK(cudaEventRecord(marks[0], s));
+   const bool multi = h->numRanks > 1;
+#define MARK(id, stream) do { if (tl) CK(cudaEventRecord(tl[id], stream)); } while (0)
+   MARK(M_START, s);
    // K1 does not use dt (only K2/K3 do, lulesh.cc:1230,1577), so at several ranks the
    // TimeIncrement chain with its min-allreduce runs on the comm stream underneath K1.
-   const bool overlap_dt = (h->numRanks > 1) && !marks;
-   if (h->numRanks == 1) {
+   if (!multi) {
       k_time_increment<<<1, 32, 0, s>>>(P.ctl, 0);
    } else {
-      cudaStream_t ts = overlap_dt ? h->comm_stream : s;
-      if (overlap_dt) {
-         CK(cudaEventRecord(h->ev_fork, s));
-         CK(cudaStreamWaitEvent(ts, h->ev_fork, 0));
-      }
+      CK(cudaEventRecord(h->ev_fork, s));
+      CK(cudaStreamWaitEvent(cs, h->ev_fork, 0));
+      MARK(C_DT_START, cs);
       if (h->p2p) {   // candidates are written into every rank's slot table over NVLink
-         k_peer_dt_post<<<1, PEER_MAX_RANKS, 0, ts>>>(P.ctl, h->d_peer_slots, h->rank, h->numRanks,
+         k_peer_dt_post<<<1, PEER_MAX_RANKS, 0, cs>>>(P.ctl, h->d_peer_slots, h->rank, h->numRanks,
                                                       &h->counters->dt_seq);
-         k_peer_dt_wait<<<1, PEER_MAX_RANKS, 0, ts>>>(P.ctl, h->dtslots, h->numRanks, &h->counters->dt_expect);
+         k_peer_dt_wait<<<1, PEER_MAX_RANKS, 0, cs>>>(P.ctl, h->dtslots, h->numRanks, &h->counters->dt_expect);
       } else {
-         k_time_increment<<<1, 32, 0, ts>>>(P.ctl, 1);
-         NK(h->nccl->AllReduce(&P.ctl->gnewdt, &P.ctl->gnewdt, 1, ncclDouble, ncclMin, h->comm, ts));
+         k_time_increment<<<1, 32, 0, cs>>>(P.ctl, 1);
+         NK(h->nccl->AllReduce(&P.ctl->gnewdt, &P.ctl->gnewdt, 1, ncclDouble, ncclMin, h->comm, cs));
       }
-      k_time_increment<<<1, 32, 0, ts>>>(P.ctl, 2);
-      if (overlap_dt) CK(cudaEventRecord(h->ev_dt, ts));
+      k_time_increment<<<1, 32, 0, cs>>>(P.ctl, 2);
+      CK(cudaEventRecord(h->ev_dt, cs));
+      MARK(C_DT_END, cs);
       h->launches += 2;
    }
-   if (marks) CK(cudaEventRecord(marks[1], s));
+   MARK(M_K1_START, s);
    k_force<<<h->k1_grid, K1_THREADS, K1_SMEM_BYTES, s>>>(P);
-   if (marks) CK(cudaEventRecord(marks[2], s));
-   if (h->numRanks > 1 && h->p2p) {
-      // Shared nodes: gather own partials -> store them into the neighbours -> wait for theirs ->
+   MARK(M_K1_END, s);
+   if (multi) {
+      // Shared nodes: gather own partials -> ship them to the neighbours -> wait for theirs ->
       // sum in rank order and advance.  The whole chain runs on the comm stream underneath the
       // interior node update (it follows the dt chain there, which boundary_update needs anyway).
-      cudaStream_t bs = overlap_dt ? h->comm_stream : s;
-      if (overlap_dt) {
-         CK(cudaEventRecord(h->ev_a, s));                 // K1 finished
-         CK(cudaStreamWaitEvent(bs, h->ev_a, 0));
+      CK(cudaEventRecord(h->ev_a, s));                 // K1 finished
+      CK(cudaStreamWaitEvent(cs, h->ev_a, 0));
+      MARK(C_NODE_START, cs);
+      k_node_boundary_gather<<<blocks_for(P.nbnode, 128), 128, 0, cs>>>(P);
+      if (h->p2p) {
+         k_peer_pack<<<blocks_for((int)h->send_total, 256), 256, 0, cs>>>(
+            P.fhalo, P.fhalo_stride, h->pack_idx, h->d_node_slot_msg, (int)h->send_total, h->d_node_msgs,
+            (int)h->msgs.size(), &h->counters->node_done, &h->counters->node_seq);
+         k_peer_wait<<<1, 32, 0, cs>>>(h->flags, PEER_FLAG_NODE, (int)h->msgs.size(), &h->counters->node_expect, P.ctl);
+         h->launches += 2;
+      } else {
+         int rc;
+         if ((rc = exchange_nodes(h, cs))) return rc;
+         h->launches += 1;
       }
-      k_node_boundary_gather<<<blocks_for(P.nbnode, 128), 128, 0, bs>>>(P);
-      k_peer_pack<<<blocks_for((int)h->send_total, 256), 256, 0, bs>>>(
-         P.fhalo, P.fhalo_stride, h->pack_idx, h->d_node_slot_msg, (int)h->send_total, h->d_node_msgs,
-         (int)h->msgs.size(), &h->counters->node_done, &h->counters->node_seq);
-      k_peer_wait<<<1, 32, 0, bs>>>(h->flags, PEER_FLAG_NODE, (int)h->msgs.size(), &h->counters->node_expect, P.ctl);
-      k_node_boundary_update<<<blocks_for(P.nbnode, 128), 128, 0, bs>>>(P, dbg);
-      if (overlap_dt) {
-         CK(cudaEventRecord(h->ev_b, bs));
-         CK(cudaStreamWaitEvent(s, h->ev_dt, 0));
-      }
-      k_node<<<blocks_for(P.nn, K2_THREADS), K2_THREADS, 0, s>>>(P, dbg);   // interior nodes
-      if (overlap_dt) CK(cudaStreamWaitEvent(s, h->ev_b, 0));
-      h->launches += 4;
-   } else if (h->numRanks > 1) {
-      int rc;
-      k_node_boundary_gather<<<blocks_for(P.nbnode, 128), 128, 0, s>>>(P);
-      if ((rc = exchange_nodes(h))) return rc;
-      if (overlap_dt) CK(cudaStreamWaitEvent(s, h->ev_dt, 0));
-      k_node<<<blocks_for(P.nn, K2_THREADS), K2_THREADS, 0, s>>>(P, dbg);   // interior, overlaps the exchange
-      CK(cudaStreamWaitEvent(s, h->ev_b, 0));
-      k_node_boundary_update<<<blocks_for(P.nbnode, 128), 128, 0, s>>>(P, dbg);
-      h->launches += 3;
-   } else {
-      k_node<<<blocks_for(P.nn, K2_THREADS), K2_THREADS, 0, s>>>(P, dbg);
-   }
-   if (marks) CK(cudaEventRecord(marks[3], s));
-   k_kinematics<<<h->k3_grid, K3_THREADS, K3_SMEM_BYTES, s>>>(P);
-   if (h->numRanks > 1 && h->p2p) {
-      k_peer_pack<<<blocks_for((int)h->mq_total, 256), 256, 0, s>>>(
-         P.delv_xi, 0, h->mq_idx, h->d_face_slot_msg, (int)h->mq_total, h->d_face_msgs,
-         (int)h->faces.size(), &h->counters->face_done, &h->counters->face_seq);
-      k_peer_wait<<<1, 32, 0, s>>>(h->flags, PEER_FLAG_FACE, (int)h->faces.size(), &h->counters->face_expect, P.ctl);
+      k_node_boundary_update<<<blocks_for(P.nbnode, 128), 128, 0, cs>>>(P, dbg);
+      CK(cudaEventRecord(h->ev_b, cs));
+      MARK(C_NODE_END, cs);
+      CK(cudaStreamWaitEvent(s, h->ev_dt, 0));
       h->launches += 2;
-   } else if (h->numRanks > 1) {
-      int rc;
-      if ((rc = exchange_monoq(h))) return rc;
-      h->launches += 1;
    }
-   if (marks) CK(cudaEventRecord(marks[4], s));
-   k_material<<<P.numWorkBlocks, MAT_THREADS, 0, s>>>(P, dbg);
-   if (marks) CK(cudaEventRecord(marks[5], s));
+   k_node<<<blocks_for(P.nn, K2_THREADS), K2_THREADS, 0, s>>>(P, dbg);   // interior nodes at several ranks
+   MARK(M_K2_END, s);
+   if (multi) CK(cudaStreamWaitEvent(s, h->ev_b, 0));
+   MARK(M_NODE_JOIN, s);
+   k_kinematics<<<h->k3_grid, K3_THREADS, K3_SMEM_BYTES, s>>>(P);
+   MARK(M_K3_END, s);
+   if (multi) {
+      // MonoQ exchange (CommMonoQ, lulesh-comm.cc:1684) on the comm stream; the elements that read
+      // no ghost slot start right away on the main stream and hide it.
+      CK(cudaEventRecord(h->ev_a, s));                 // K3 finished
+      CK(cudaStreamWaitEvent(cs, h->ev_a, 0));
+      MARK(C_MQ_START, cs);
+      if (h->p2p) {
+         k_peer_pack<<<blocks_for((int)h->mq_total, 256), 256, 0, cs>>>(
+            P.delv_xi, 0, h->mq_idx, h->d_face_slot_msg, (int)h->mq_total, h->d_face_msgs,
+            (int)h->faces.size(), &h->counters->face_done, &h->counters->face_seq);
+         k_peer_wait<<<1, 32, 0, cs>>>(h->flags, PEER_FLAG_FACE, (int)h->faces.size(), &h->counters->face_expect, P.ctl);
+         h->launches += 2;
+      } else {
+         int rc;
+         if ((rc = exchange_monoq(h, cs))) return rc;
+         h->launches += 1;
+      }
+      CK(cudaEventRecord(h->ev_b, cs));
+      MARK(C_MQ_END, cs);
+      if (P.numWorkBlocksInterior > 0)
+         (P.unit_rho0 ? k_material : k_material_rho0)<<<P.numWorkBlocksInterior, MAT_THREADS, 0, s>>>(P, dbg, 0);
+      MARK(M_K45I_END, s);
+      CK(cudaStreamWaitEvent(s, h->ev_b, 0));
+      MARK(M_MONOQ_JOIN, s);
+      if (P.numWorkBlocks > P.numWorkBlocksInterior)
+         (P.unit_rho0 ? k_material : k_material_rho0)<<<P.numWorkBlocks - P.numWorkBlocksInterior, MAT_THREADS, 0, s>>>(P, dbg, P.numWorkBlocksInterior);
+      h->launches += 1;
+   } else {
+      MARK(M_K45I_END, s);
+      MARK(M_MONOQ_JOIN, s);
+      (P.unit_rho0 ? k_material : k_material_rho0)<<<P.numWorkBlocks, MAT_THREADS, 0, s>>>(P, dbg, 0);
+   }
+   MARK(M_END, s);
+#undef MARK
    h->launches += 5;
    CK(cudaGetLastError());
+   return 0;
+}
+
+// NCCL sets up its connections lazily, at the first operation between two ranks -- allocations
+// and IPC traffic that are illegal under stream capture.  One eager pass over the three exchange
+// patterns of a cycle (all of them write scratch only: gnewdt, fhalo receive slots, ghost slots)
+// leaves nothing to set up when the cycle is captured.
+static int warm_nccl(lulesh_b200 *h)
+{
+   int rc;
+   cudaStream_t cs = h->comm_stream;
+   CK(cudaStreamSynchronize(h->stream));
+   NK(h->nccl->AllReduce(&h->P.ctl->gnewdt, &h->P.ctl->gnewdt, 1, ncclDouble, ncclMin, h->comm, cs));
+   if ((rc = exchange_nodes(h, cs))) return rc;
+   if ((rc = exchange_monoq(h, cs))) return rc;
+   CK(cudaStreamSynchronize(cs));
+   h->launches -= 2;
+   h->nccl_warm = true;
    return 0;
 }
 
@@ -1130,10 +1186,14 @@ static int ensure_graph(lulesh_b200 *h)
 {
    if (h->graph && h->graph_debug == h->debug) return 0;
    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+   const bool nccl_cycle = h->numRanks > 1 && !h->p2p;
+   int rc;
+   if (nccl_cycle && !h->nccl_warm && (rc = warm_nccl(h))) return rc;
    cudaGraph_t g;
    const int64_t saved = h->launches;
-   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-   int rc = enqueue_cycle(h, nullptr);
+   // NCCL's enqueue path may touch the CUDA API from its own helper thread
+   CK(cudaStreamBeginCapture(h->stream, nccl_cycle ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
+   rc = enqueue_cycle(h, nullptr);
    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
    h->launches_per_cycle = (int)(h->launches - saved);
    h->launches = saved;
@@ -1147,14 +1207,15 @@ static int ensure_graph(lulesh_b200 *h)
 
 static bool use_graph(const lulesh_b200 *h)
 {
-   // A cycle is captured once and replayed: 5 kernels at one rank; kernels + peer-to-peer
-   // exchange kernels on two streams at several ranks.  With the NCCL fallback the cycle is
-   // launched eagerly (NCCL 2.28 reported an internal error when its first collective was
-   // issued under capture on the forked stream; LULESH_B200_MULTI_GRAPH=1 opts in).
+   // A cycle is captured once and replayed: 5 kernels at one rank; kernels + exchange on two
+   // streams at several ranks (peer-to-peer kernels, or NCCL send/recv + allreduce after an
+   // eager warm-up pass).  LULESH_B200_NO_GRAPH=1 launches every cycle eagerly;
+   // LULESH_B200_NCCL_GRAPH=0 does so for the NCCL cycle only.
    static const bool disabled = getenv("LULESH_B200_NO_GRAPH") != nullptr;
-   static const bool multi_enabled = getenv("LULESH_B200_MULTI_GRAPH") != nullptr;
+   static const char *ng = getenv("LULESH_B200_NCCL_GRAPH");
+   static const bool nccl_graph = !(ng && ng[0] == '0');
    if (disabled) return false;
-   return h->numRanks == 1 || h->p2p || multi_enabled;
+   return h->numRanks == 1 || h->p2p || nccl_graph;
 }
 
 static int enqueue_cycles(lulesh_b200 *h, int n)
@@ -1178,18 +1239,18 @@ static int fetch_ctl(lulesh_b200 *h)
    return 0;
 }
 
-// New cycle limit for the device-side loop condition (lulesh.cc:2745).  `skip_force` is that
-// condition evaluated one cycle ahead (see k_time_increment), so it is re-derived here from the
-// current time and cycle.
+// New cycle limit for the device-side loop condition (lulesh.cc:2745).  If the loop can go on
+// under the new limit, `done` is cleared here, before any cycle is enqueued: the force kernel
+// reads it concurrently with the dt chain that would otherwise clear it (see k_force).
 static int set_max_cycles(lulesh_b200 *h, int max_cycles)
 {
    int rc;
    if ((rc = fetch_ctl(h))) return rc;
    const Ctl &c = *h->h_ctl;
-   const int v[2] = {max_cycles, (c.time < c.stoptime && c.cycle < max_cycles) ? 0 : 1};
-   CK(cudaMemcpyAsync(&h->P.ctl->max_cycles, &v[0], sizeof(int), cudaMemcpyHostToDevice, h->stream));
-   CK(cudaMemcpyAsync(&h->P.ctl->skip_force, &v[1], sizeof(int), cudaMemcpyHostToDevice, h->stream));
-   CK(cudaStreamSynchronize(h->stream));   // v[] is a stack array
+   CK(cudaMemcpyAsync(&h->P.ctl->max_cycles, &max_cycles, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+   if (c.error == 0 && c.time < c.stoptime && c.cycle < max_cycles)
+      CK(cudaMemsetAsync(&h->P.ctl->done, 0, sizeof(int), h->stream));
+   CK(cudaStreamSynchronize(h->stream));   // max_cycles is a stack variable
    return 0;
 }
 
@@ -1206,8 +1267,7 @@ extern "C" int lulesh_b200_sum_nodal_mass(lulesh_b200 *h)
       k_gather_index<<<blocks_for(P.nbnode, 256), 256, 0, h->stream>>>(
          P.fhalo + (size_t)a * P.nbnode, mass, P.bnode, P.nbnode);
    int rc;
-   if ((rc = exchange_nodes(h))) return rc;
-   CK(cudaStreamWaitEvent(h->stream, h->ev_b, 0));
+   if ((rc = exchange_nodes(h, h->stream))) return rc;
    k_boundary_mass<<<blocks_for(P.nbnode, 128), 128, 0, h->stream>>>(P, mass);
    CK(cudaStreamSynchronize(h->stream));   // doubles as the MPI_Barrier of lulesh.cc:2732
    return 0;
@@ -1244,6 +1304,56 @@ extern "C" int lulesh_b200_step(lulesh_b200 *h)
    return h->h_ctl->error;
 }
 
+// Average per-cycle timeline over `cycles` eagerly launched cycles (same schedule and stream
+// layout as the graph: nothing is serialised for the measurement).
+static int run_timeline(lulesh_b200 *h, int cycles, float *out)
+{
+   int rc;
+   cudaEvent_t ev[TL_EVENTS];
+   for (auto &e : ev) CK(cudaEventCreate(&e));
+   double acc[LULESH_B200_TIMELINE_N] = {0};
+   const bool multi = h->numRanks > 1;
+   auto span = [&](int a, int b, double *dst) -> int {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, ev[a], ev[b]));
+      *dst += ms;
+      return 0;
+   };
+   for (int i = 0; i < cycles; ++i) {
+      if ((rc = enqueue_cycle(h, ev))) return rc;
+      CK(cudaStreamSynchronize(h->stream));
+      if (multi) CK(cudaStreamSynchronize(h->comm_stream));
+      if ((rc = span(M_START, M_K1_START, &acc[LULESH_TL_TIME_INCREMENT]))) return rc;
+      if ((rc = span(M_K1_START, M_K1_END, &acc[LULESH_TL_K1]))) return rc;
+      if ((rc = span(M_K1_END, M_K2_END, &acc[LULESH_TL_K2]))) return rc;
+      if ((rc = span(M_K2_END, M_NODE_JOIN, &acc[LULESH_TL_NODE_JOIN_WAIT]))) return rc;
+      if ((rc = span(M_NODE_JOIN, M_K3_END, &acc[LULESH_TL_K3]))) return rc;
+      if ((rc = span(M_K3_END, M_K45I_END, &acc[LULESH_TL_K45_INTERIOR]))) return rc;
+      if ((rc = span(M_K45I_END, M_MONOQ_JOIN, &acc[LULESH_TL_MONOQ_JOIN_WAIT]))) return rc;
+      if ((rc = span(M_MONOQ_JOIN, M_END, &acc[LULESH_TL_K45_TAIL]))) return rc;
+      if ((rc = span(M_START, M_END, &acc[LULESH_TL_CYCLE]))) return rc;
+      if (multi) {
+         if ((rc = span(C_DT_START, C_DT_END, &acc[LULESH_TL_COMM_DT]))) return rc;
+         if ((rc = span(C_NODE_START, C_NODE_END, &acc[LULESH_TL_COMM_NODE]))) return rc;
+         if ((rc = span(C_MQ_START, C_MQ_END, &acc[LULESH_TL_COMM_MONOQ]))) return rc;
+      }
+   }
+   for (auto &e : ev) cudaEventDestroy(e);
+   for (int k = 0; k < LULESH_B200_TIMELINE_N; ++k) out[k] = cycles > 0 ? (float)(acc[k] / cycles) : 0.f;
+   return 0;
+}
+
+extern "C" int lulesh_b200_timeline(lulesh_b200 *h, int32_t cycles, float *out_ms)
+{
+   if (!h || cycles < 1 || !out_ms) return fail(LULESH_B200_EINVAL, "bad argument");
+   CK(cudaSetDevice(h->device));
+   int rc;
+   if ((rc = set_max_cycles(h, INT_MAX))) return rc;
+   if ((rc = run_timeline(h, cycles, out_ms))) return rc;
+   if ((rc = fetch_ctl(h))) return rc;
+   return h->h_ctl->error;
+}
+
 extern "C" int lulesh_b200_time_cycles(lulesh_b200 *h, int32_t cycles, float *total_ms,
                                        float *per_kernel_ms, int64_t *launches)
 {
@@ -1261,22 +1371,15 @@ extern "C" int lulesh_b200_time_cycles(lulesh_b200 *h, int32_t cycles, float *to
       CK(cudaStreamSynchronize(h->stream));
       if (total_ms) CK(cudaEventElapsedTime(total_ms, h->ev_t0, h->ev_t1));
    } else {
-      cudaEvent_t marks[6];
-      for (auto &m : marks) CK(cudaEventCreate(&m));
-      for (int k = 0; k < LULESH_B200_NUM_KERNELS; ++k) per_kernel_ms[k] = 0.f;
-      float total = 0.f;
-      for (int i = 0; i < cycles; ++i) {
-         if ((rc = enqueue_cycle(h, marks))) return rc;
-         CK(cudaStreamSynchronize(h->stream));
-         for (int k = 0; k < LULESH_B200_NUM_KERNELS; ++k) {
-            float ms;
-            CK(cudaEventElapsedTime(&ms, marks[k], marks[k + 1]));
-            per_kernel_ms[k] += ms;
-            total += ms;
-         }
-      }
-      for (auto &m : marks) cudaEventDestroy(m);
-      if (total_ms) *total_ms = total;
+      float tl[LULESH_B200_TIMELINE_N];
+      if ((rc = run_timeline(h, cycles, tl))) return rc;
+      // the five main-stream intervals of a cycle (waits for the comm stream included)
+      per_kernel_ms[0] = tl[LULESH_TL_TIME_INCREMENT] * cycles;
+      per_kernel_ms[1] = tl[LULESH_TL_K1] * cycles;
+      per_kernel_ms[2] = (tl[LULESH_TL_K2] + tl[LULESH_TL_NODE_JOIN_WAIT]) * cycles;
+      per_kernel_ms[3] = tl[LULESH_TL_K3] * cycles;
+      per_kernel_ms[4] = (tl[LULESH_TL_K45_INTERIOR] + tl[LULESH_TL_MONOQ_JOIN_WAIT] + tl[LULESH_TL_K45_TAIL]) * cycles;
+      if (total_ms) *total_ms = tl[LULESH_TL_CYCLE] * cycles;
    }
    if (launches) *launches = h->launches - l0;
    if ((rc = fetch_ctl(h))) return rc;
@@ -1314,7 +1417,7 @@ extern "C" int lulesh_b200_set_scalars(lulesh_b200 *h, const lulesh_b200_scalars
    c.deltatimemultlb = in->deltatimemultlb; c.deltatimemultub = in->deltatimemultub;
    c.dtmax = in->dtmax; c.stoptime = in->stoptime; c.cycle = in->cycle; c.error = in->error;
    c.done = 0;
-   c.skip_force = (c.time < c.stoptime && c.cycle < c.max_cycles) ? 0 : 1;
+   c.pending_error = 0;
    CK(cudaMemcpy(h->P.ctl, &c, sizeof c, cudaMemcpyHostToDevice));
    return 0;
 }
@@ -1378,7 +1481,14 @@ extern "C" int lulesh_b200_kernel_force(lulesh_b200 *h)
    if (!h) return fail(LULESH_B200_EINVAL, "null handle");
    CK(cudaSetDevice(h->device));
    k_force<<<h->k1_grid, K1_THREADS, K1_SMEM_BYTES, h->stream>>>(h->P);
-   return finish_kernel(h);
+   int rc = finish_kernel(h);
+   if (rc == 0 && h->h_ctl->pending_error != 0) {   // standalone launch: promote K1's abort test here (k_node does it in a cycle)
+      rc = h->h_ctl->pending_error;
+      const int v[2] = {rc, 0};
+      CK(cudaMemcpy(&h->P.ctl->error, &v[0], sizeof(int), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(&h->P.ctl->pending_error, &v[1], sizeof(int), cudaMemcpyHostToDevice));
+   }
+   return rc;
 }
 
 extern "C" int lulesh_b200_kernel_node(lulesh_b200 *h, int materialise_debug)
@@ -1403,7 +1513,7 @@ extern "C" int lulesh_b200_kernel_material(lulesh_b200 *h)
    if (!h) return fail(LULESH_B200_EINVAL, "null handle");
    if (h->numRanks != 1) return fail(LULESH_B200_EINVAL, "per-kernel entry points are single-rank");
    CK(cudaSetDevice(h->device));
-   k_material<<<h->P.numWorkBlocks, MAT_THREADS, 0, h->stream>>>(h->P, 1);
+   (h->P.unit_rho0 ? k_material : k_material_rho0)<<<h->P.numWorkBlocks, MAT_THREADS, 0, h->stream>>>(h->P, 1, 0);
    return finish_kernel(h);
 }
 

@@ -25,7 +25,9 @@ enum : int {
    ETA_M = 0x001c0, ETA_M_SYMM = 0x00040, ETA_M_FREE = 0x00080,
    ETA_P = 0x00e00, ETA_P_SYMM = 0x00200, ETA_P_FREE = 0x00400,
    ZETA_M = 0x07000, ZETA_M_SYMM = 0x01000, ZETA_M_FREE = 0x02000,
-   ZETA_P = 0x38000, ZETA_P_SYMM = 0x08000, ZETA_P_FREE = 0x10000
+   ZETA_P = 0x38000, ZETA_P_SYMM = 0x08000, ZETA_P_FREE = 0x10000,
+   XI_M_COMM = 0x00004, XI_P_COMM = 0x00020, ETA_M_COMM = 0x00100, ETA_P_COMM = 0x00800,
+   ZETA_M_COMM = 0x04000, ZETA_P_COMM = 0x20000
 };
 
 // per-node flag byte built at create() from symmX/Y/Z and the halo layout
@@ -42,7 +44,7 @@ struct Ctl {
    int cycle, max_cycles;
    int done;             // 1: time >= stoptime or cycle >= max_cycles -> kernels no-op
    int error;            // sticky, first one wins: 0 / VolumeError -1 / QStopError -2 / infrastructure
-   int skip_force;       // `done` of the NEXT cycle, for the kernels that run next to its dt chain
+   int pending_error;    // K1's abort test, promoted to `error` by K2 if the cycle is live
 };
 
 struct KParams {
@@ -67,6 +69,7 @@ struct KParams {
    const int *workElem;           // [numWorkBlocks*MAT_THREADS], -1 = padding
    const int *workBlockRep;       // [numWorkBlocks] EOS repetition count of the block's region
    int numWorkBlocks;
+   int numWorkBlocksInterior;     // blocks [0, interior) never read ghost slots; the rest wait for the MonoQ exchange
    // multi-rank boundary-node machinery (null/0 at numRanks==1)
    int nbnode;                    // boundary (shared) nodes on this rank
    const int *bnode;              // [nbnode] node id
@@ -75,7 +78,7 @@ struct KParams {
    double *fhalo;                 // [3][fhalo_stride]: own partials [0,nbnode) then recv slots
    int fhalo_stride;
    const struct PeerCounters *peer_cnt;   // non-null in peer-to-peer mode: fhalo is double-buffered by sequence parity
-   int unit_rho0;                 // refdens == 1.0: EOS skips the exact no-op division
+   int unit_rho0;                 // refdens == 1.0: k_material (no division by rho0) instead of k_material_rho0
    lulesh_b200_constants c;
 };
 
@@ -106,7 +109,8 @@ __global__ void k_node(const KParams P, int storeDebug);
 __global__ void k_node_boundary_gather(const KParams P);
 __global__ void k_node_boundary_update(const KParams P, int storeDebug);
 __global__ void k_kinematics(const KParams P);
-__global__ void k_material(const KParams P, int storeQ);
+__global__ void k_material(const KParams P, int storeQ, int firstBlock);
+__global__ void k_material_rho0(const KParams P, int storeQ, int firstBlock);
 __global__ void k_gather_index(double *dst, const double *src, const int *idx, int n);
 
 // ---- peer-to-peer halo exchange over NVLink (stores into the neighbour's HBM + flags)

@@ -19,7 +19,11 @@ Outputs (committed):
                                   locations of a 2x2x2 layout (lulesh-init.cc)
 `--long` also runs -s 45/-s 60 to stoptime (minutes).  The -s 90 and -s 128
 records were produced with the same binary (`-r 1 -c 0`, results are region
-independent) and are merged from /tmp/gold/*.out when present.
+independent) and are merged from /tmp/gold/*.out when present, and so
+are the config-3-size records (16.8 M elements, ~16 GB, 6 s per cycle on 6 cores):
+
+    OMP_NUM_THREADS=6 oracle/_ref/lulesh_omp -s 256 -i 10 -r 1 -c 0 > /tmp/gold/s256_i10.out
+    OMP_NUM_THREADS=6 oracle/_ref/lulesh_omp -s 256 -i 40 -r 1 -c 0 > /tmp/gold/s256_i40.out
 """
 import io, json, os, subprocess, sys
 import numpy as np
@@ -106,6 +110,14 @@ def main():
                     rec = json.loads(line[len("REFJSON "):])
                     rec.pop("elapsed", None)
                     gold[f"lulesh_omp -s {rec['nx']} -r 1 -c 0"] = rec
+    for tag in ("s256_i10", "s256_i40"):
+        p = f"/tmp/gold/{tag}.out"
+        if os.path.exists(p):
+            for line in open(p):
+                if line.startswith("REFJSON "):
+                    rec = json.loads(line[len("REFJSON "):])
+                    rec.pop("elapsed", None)
+                    gold[f"lulesh_omp -s {rec['nx']} -i {rec['cycles']} -r 1 -c 0"] = rec
     json.dump(gold, open(path, "w"), indent=1, sort_keys=True)
 
     for cyc in (9, 10):

@@ -22,6 +22,21 @@ def test_reference_arm_json_line():
     assert d["config"]["workload"].startswith("-s 12 ")
 
 
+def test_reference_arm_never_loads_the_product_library(tmp_path):
+    """The arm must run with no product library at all, and echo steps/warmup/config like the b200 arm."""
+    env = dict(os.environ, LULESH_B200_LIB=str(tmp_path / "missing.so"))
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "10",
+                        "--steps", "7", "--warmup", "4"], capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stderr
+    d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][0])
+    assert d["steps"] == 7 and d["warmup"] == 4
+    sys.path.insert(0, ROOT)
+    import bench
+    args = bench.argparse.Namespace(size=10, glob=0, regions=11, balance=1, cost=1, steps=7, warmup=4)
+    assert d["config"] == bench.workload_config(args, 1)     # same dict as the b200 arm prints
+    assert "lulesh_b200" not in " ".join(d["cpu_baseline"]["sample"].split("lulesh_omp"))
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
@@ -37,3 +52,11 @@ def test_helpers():
     peak, src = bench.measured_peak_gbs()
     assert 3000 < peak < 9000 and ("measured" in src or "fallback" in src)
     assert sum(v for k, v in bench.B_ALG.items()) == bench.B_ALG_STEP
+    assert bench.decompose(1) == (1, 1, 1) and bench.decompose(2) == (1, 1, 2)
+    assert bench.decompose(4) == (1, 2, 2) and bench.decompose(8) == (2, 2, 2) and bench.decompose(27) == (3, 3, 3)
+    import lulesh_b200 as lb
+    for n in (1, 2, 4, 8, 27):
+        assert bench.decompose(n) == lb.decompose(n)          # the restated rule is the library's
+    ns = bench.argparse.Namespace(size=0, glob=384, regions=11, balance=1, cost=1, steps=5, warmup=3)
+    assert bench.rank_sizes(ns, 4) == ((1, 2, 2), (384, 192, 192))
+    assert bench.reference_sample_size(256, 8, 10 ** 6, 1.0) <= 32

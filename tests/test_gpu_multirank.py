@@ -144,3 +144,69 @@ def test_two_rank_driver_binary(lb, goldens):
     gold = goldens["lulesh_omp -s 20"]
     assert rec["cycles"] == gold["cycles"]
     assert abs(rec["e0"] - gold["e0"]) <= 1e-8 * gold["e0"]
+
+
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+def test_two_rank_progress_run_to_stoptime(lb, goldens, halo):
+    """`-p` on several GPUs (rank 0 prints every cycle, lulesh.cc:2750): every rank must enqueue the
+    same number of cycles or the others wait for exchanges that never come.  -s 30 ends at cycle
+    932, which is not a multiple of the default batch of 64."""
+    if ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = {"LULESH_B200_FULL_PRECISION": "1", "PATH": "/usr/bin:/bin"}
+    if halo == "nccl":
+        env["LULESH_B200_HALO"] = "nccl"
+    p = subprocess.run([lb.BIN_PATH, "--gpus", "2", "--global", "30", "-p"], capture_output=True, text=True,
+                       env=env, timeout=240)
+    assert p.returncode == 0, p.stderr + p.stdout[-2000:]
+    gold = goldens["lulesh_omp -s 30 -r 1 -c 0"]
+    assert len([l for l in p.stdout.splitlines() if l.startswith("cycle = ")]) == gold["cycles"]
+    rec = json.loads([l for l in p.stdout.splitlines() if l.startswith("B200JSON ")][0][9:])
+    assert rec["cycles"] == gold["cycles"]
+    assert abs(rec["e0"] - gold["e0"]) <= 1e-8 * gold["e0"]
+
+
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+def test_error_on_one_rank_stops_every_rank(lb, halo, monkeypatch):
+    """A VolumeError on one rank (the reference calls MPI_Abort(-1), lulesh.cc:1038) travels with the
+    dt reduction: all ranks return -1 from the same cycle, promptly, instead of timing out on
+    exchanges the failed rank no longer feeds."""
+    if ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import time
+    if halo == "nccl":
+        monkeypatch.setenv("LULESH_B200_HALO", "nccl")
+    else:
+        monkeypatch.delenv("LULESH_B200_HALO", raising=False)
+    decomp, sizes, n = (1, 1, 2), (10, 10, 5), 2
+    uid = lb.get_unique_id()
+    res, errs = [None] * n, []
+
+    def body(r):
+        try:
+            dom = lb.Domain(sizes[0], num_ranks=n, rank=r, decomp=decomp, sizes=sizes)
+            dev = lb.Device(dom, device=r, unique_id=uid)
+            dev.sum_nodal_mass()
+            dev.run(20)
+            if r == 1:   # a negative relative volume on rank 1 only
+                v = dev.download("v")
+                v[3] = -1.0
+                dev.upload("v", v)
+            t0 = time.perf_counter()
+            try:
+                dev.run(200)
+                code = 0
+            except lb.LuleshError as ex:
+                code = ex.code
+            res[r] = (code, dev.scalars.cycle, time.perf_counter() - t0)
+            dev.close()
+        except Exception as ex:   # pragma: no cover
+            errs.append(ex)
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    assert [c for c, _, _ in res] == [lb.VOLUME_ERROR, lb.VOLUME_ERROR], res
+    assert res[0][1] == res[1][1] and 20 <= res[0][1] <= 22, res     # same cycle on both ranks
+    assert max(t for _, _, t in res) < 3.0, res                        # no 4 s spin time-outs
