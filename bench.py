@@ -545,6 +545,7 @@ def main():
     sampler = ClockSampler(job.local) if rank == 0 else None
     if sampler:
         sampler.wait_ready()
+    job.barrier()   # rank 0 may have waited seconds for nvidia-smi; the ranks of a cycle must start together
     ms, launches = job.timed(dev, args.warmup, args.steps)
     clocks = sampler.stop() if sampler else None
     value = ne_total * args.steps / (ms * 1e-3)
@@ -629,7 +630,7 @@ def main():
         nccl_fallback = {"halo": dev3.halo_mode, "value": ne_total * args.steps / (ms3 * 1e-3),
                          "ms_per_step": ms3 / args.steps,
                          "what": "same workload with ncclSend/ncclRecv halo exchange and ncclAllReduce(min) for dt "
-                                 "(LULESH_B200_HALO=nccl), the cycle replayed from a CUDA graph"}
+                                 "(LULESH_B200_HALO=nccl), cycles launched eagerly on two streams"}
         dev3.close()
     del dom
     if n > 1 and not args.no_parity:

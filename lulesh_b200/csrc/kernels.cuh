@@ -45,6 +45,7 @@ struct Ctl {
    int done;             // 1: time >= stoptime or cycle >= max_cycles -> kernels no-op
    int error;            // sticky, first one wins: 0 / VolumeError -1 / QStopError -2 / infrastructure
    int pending_error;    // K1's abort test, promoted to `error` by K2 if the cycle is live
+   int zero;             // always 0; loaded by the EOS loop so that its repetitions cannot be folded
 };
 
 struct KParams {
@@ -99,9 +100,15 @@ constexpr int K1_BLOCKS_PER_SM = LB_K1_BPS;
 constexpr int K2_THREADS = 256;
 constexpr int K3_THREADS = LB_K3_THREADS;
 constexpr int K3_BLOCKS_PER_SM = LB_K3_BPS;
-constexpr int K1_SMEM_BYTES = 54 * K1_THREADS * 8;   // cp.async staging tile: 48 node values + 6 scalars
+#ifdef LB_K1_LEAN
+constexpr int K1_SLOTS = 72;   // cp.async staging tile (48 node values + 6 scalars) + 18 parked face-stress values
+#else
+constexpr int K1_SLOTS = 54;   // cp.async staging tile: 48 node values + 6 scalars
+#endif
+constexpr int K1_SMEM_BYTES = K1_SLOTS * K1_THREADS * 8;
 constexpr int K3_SMEM_BYTES = 50 * K3_THREADS * 8;   // 48 node values + volo, v
 constexpr int MAT_THREADS = 128;
+constexpr int MAT_BLOCKS_PER_SM = 8;
 
 __global__ void k_time_increment(Ctl *ctl, int phase);
 __global__ void k_force(const KParams P);
