@@ -100,11 +100,7 @@ constexpr int K1_BLOCKS_PER_SM = LB_K1_BPS;
 constexpr int K2_THREADS = 256;
 constexpr int K3_THREADS = LB_K3_THREADS;
 constexpr int K3_BLOCKS_PER_SM = LB_K3_BPS;
-#ifdef LB_K1_LEAN
-constexpr int K1_SLOTS = 72;   // cp.async staging tile (48 node values + 6 scalars) + 18 parked face-stress values
-#else
 constexpr int K1_SLOTS = 54;   // cp.async staging tile: 48 node values + 6 scalars
-#endif
 constexpr int K1_SMEM_BYTES = K1_SLOTS * K1_THREADS * 8;
 constexpr int K3_SMEM_BYTES = 50 * K3_THREADS * 8;   // 48 node values + volo, v
 constexpr int MAT_THREADS = 128;
