@@ -245,11 +245,11 @@ enum lulesh_b200_timeline_slot {
    LULESH_TL_K3,                  /* kinematics + monotonic-Q gradients                 */
    LULESH_TL_K45_INTERIOR,        /* material kernel over elements without ghost reads  */
    LULESH_TL_MONOQ_JOIN_WAIT,     /* main stream waiting for the MonoQ exchange         */
-   LULESH_TL_K45_TAIL,            /* material kernel over the remaining elements        */
+   LULESH_TL_K45_TAIL,            /* 0: the face-layer launch runs on the comm stream   */
    LULESH_TL_CYCLE,               /* whole cycle, main stream                           */
    LULESH_TL_COMM_DT,             /* comm stream: dt candidate, min over ranks, K6      */
    LULESH_TL_COMM_NODE,           /* comm stream: shared-node gather, exchange, update  */
-   LULESH_TL_COMM_MONOQ,          /* comm stream: MonoQ pack, exchange                  */
+   LULESH_TL_COMM_MONOQ,          /* comm stream: MonoQ pack, exchange, K45 face layer  */
    LULESH_B200_TIMELINE_N
 };
 int lulesh_b200_timeline(lulesh_b200 *h, int32_t cycles, float *out_ms /* [LULESH_B200_TIMELINE_N] */);

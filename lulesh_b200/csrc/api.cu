@@ -1142,6 +1142,12 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *tl)
          if ((rc = exchange_monoq(h, cs))) return rc;
          h->launches += 1;
       }
+      // The face-layer elements follow the exchange on the comm stream itself: a few hundred blocks
+      // whose run time is the latency of one block (up to 10 (1 + cost) EOS repetitions), hidden
+      // under the interior launch instead of trailing it.  Both launches merge their dt minima
+      // with the same integer atomicMin.
+      if (P.numWorkBlocks > P.numWorkBlocksInterior)
+         (P.unit_rho0 ? k_material : k_material_rho0)<<<P.numWorkBlocks - P.numWorkBlocksInterior, MAT_THREADS, 0, cs>>>(P, dbg, P.numWorkBlocksInterior);
       CK(cudaEventRecord(h->ev_b, cs));
       MARK(C_MQ_END, cs);
       if (P.numWorkBlocksInterior > 0)
@@ -1149,8 +1155,6 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *tl)
       MARK(M_K45I_END, s);
       CK(cudaStreamWaitEvent(s, h->ev_b, 0));
       MARK(M_MONOQ_JOIN, s);
-      if (P.numWorkBlocks > P.numWorkBlocksInterior)
-         (P.unit_rho0 ? k_material : k_material_rho0)<<<P.numWorkBlocks - P.numWorkBlocksInterior, MAT_THREADS, 0, s>>>(P, dbg, P.numWorkBlocksInterior);
       h->launches += 1;
    } else {
       MARK(M_K45I_END, s);

@@ -3,7 +3,7 @@
 # driver launches it (torchrun, one rank per GPU) at the default size and at -s 128 per GPU.
 N=${1:-2}; out=gpurun_out/${2:-r02_multi$N}; mkdir -p $out
 nvidia-smi topo -m > $out/topo.txt 2>&1
-(timeout 900 python -m pytest tests/test_gpu_multirank.py -m gpu -q --timeout 400 > $out/pytest_multi.log 2>&1; echo "pytest exit $?" >> $out/pytest_multi.log)
+(timeout 600 python -m pytest tests/test_gpu_multirank.py -m gpu -q -x --timeout 150 --timeout-method=thread > $out/pytest_multi.log 2>&1; echo "pytest exit $?" >> $out/pytest_multi.log)
 tail -n 4 $out/pytest_multi.log
 run() { timeout -k 10 ${STEP_TIMEOUT:-420} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N "$@"; }
 run --steps 20 --warmup 5 > $out/bench_n$N.json 2> $out/bench_n$N.err; echo "bench rc $?"
