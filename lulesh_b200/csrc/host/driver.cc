@@ -284,6 +284,8 @@ extern "C" int lulesh_host_main(int argc, char **argv)
       st.status = lulesh_b200_run(st.handle, opts.its, show ? 1 : opts.syncEvery,
                                   (show && r == 0) ? progress : NULL, NULL);   // lulesh.cc:2745-2757
       st.elapsed = wallclock() - t_start;
+      if (st.status != 0 && st.status != LULESH_B200_VOLUME_ERROR && st.status != LULESH_B200_QSTOP_ERROR)
+         fprintf(stderr, "lulesh_b200 (rank %d): run failed with status %d: %s\n", r, st.status, lulesh_b200_last_error());
       pthread_barrier_wait(&barrier);
    };
    if (numRanks == 1) body(0);

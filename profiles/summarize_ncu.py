@@ -27,6 +27,12 @@ METRICS = [
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall_wait"),
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall_math"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall_not_selected"),
+    ("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed", "dadd_pc"),
+    ("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed", "dmul_pc"),
+    ("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed", "dfma_pc"),
+    ("smsp__cycles_elapsed.max", "cycles"),
 ]
 
 
@@ -62,13 +68,14 @@ def main():
     json.dump(out, open(os.path.join(HERE, f"{tag}_ncu_summary.json"), "w"), indent=1)
     ne = size ** 3
     lines = [f"# ncu --set full summary `{os.path.basename(rep)}` (-s {size}, {ne} elements, one launch each)", "",
-             "| kernel | time us | DRAM read MB | DRAM write MB | DRAM B/zone | DRAM % | FP64 pipe % | issue % | warps % | regs | grid x block | warp inst | L1 hit % | L2 hit % | stall long_sb / wait / math |",
-             "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+             "| kernel | time us | DRAM read MB | DRAM write MB | DRAM B/zone | DRAM % | FP64 pipe % | issue % | warps % | regs | grid x block | warp inst | DADD+DMUL+DFMA / zone | L1 hit % | L2 hit % | stall long_sb / wait / math |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for k, r in out.items():
         lines.append(f"| {k} | {r['time_us']:.1f} | {r['dram_read_bytes']/1e6:.1f} | {r['dram_write_bytes']/1e6:.1f} | "
                      f"{r['dram_bytes']/ne:.0f} | {r.get('dram_pct',0):.1f} | {r.get('fp64_pipe_pct',0):.1f} | "
                      f"{r.get('issue_active_pct',0):.1f} | {r.get('warps_active_pct',0):.1f} | {r.get('regs',0):.0f} | "
                      f"{r.get('grid',0):.0f} x {r.get('block',0):.0f} | {r.get('warp_inst',0):.3g} | "
+                     f"{(r.get('dadd_pc',0) + r.get('dmul_pc',0) + r.get('dfma_pc',0)) * r.get('cycles',0) / ne:.0f} | "
                      f"{r.get('l1_hit_pct',0):.1f} | {r.get('l2_hit_pct',0):.1f} | "
                      f"{r.get('stall_long_sb',0):.2f} / {r.get('stall_wait',0):.2f} / {r.get('stall_math',0):.2f} |")
     lines += ["", "Times are under the profiler (cold caches, serialised); bench.py reports the live CUDA-event times.", ""]

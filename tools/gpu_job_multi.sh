@@ -7,6 +7,19 @@ nvidia-smi topo -m > $out/topo.txt 2>&1
 tail -n 4 $out/pytest_multi.log
 run() { timeout -k 10 ${STEP_TIMEOUT:-420} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N "$@"; }
 run --steps 20 --warmup 5 > $out/bench_n$N.json 2> $out/bench_n$N.err; echo "bench rc $?"
+if [ "$N" = 8 ]; then   # the 4-rank layout on the same box: parity + weak numbers, no extras
+   N=4; run --steps 20 --warmup 5 --no-extras > $out/bench_n4.json 2> $out/bench_n4.err; echo "bench n4 rc $?"; N=8
+   python - $out <<'PY'
+import json, sys
+try:
+    d = json.load(open(f"{sys.argv[1]}/bench_n4.json"))
+    p = d.get("parity") or {}
+    print("N=4 s256: %.3f Gz/s %.3f ms/step parity %s" % (d["value"]/1e9, d["ms_per_step"], p.get("status")),
+          {m: r.get("ok") for m, r in (p.get("modes") or {}).items()})
+except Exception as e:
+    print("bench_n4 unreadable", e)
+PY
+fi
 run --size 128 --steps 200 --warmup 10 --no-extras --no-parity > $out/bench_n${N}_s128.json 2> $out/bench_n${N}_s128.err; echo "bench s128 rc $?"
 LULESH_B200_HALO=nccl run --size 128 --steps 200 --warmup 10 --no-extras --no-parity > $out/bench_n${N}_s128_nccl.json 2> $out/bench_n${N}_s128_nccl.err; echo "bench s128 nccl rc $?"
 timeout 300 python bench.py --size 128 --steps 200 --warmup 10 --no-extras --no-cpu-baseline > $out/bench_n1_s128.json 2> $out/bench_n1_s128.err
