@@ -163,7 +163,6 @@ struct lulesh_b200 {
    DtSlot **d_peer_slots = nullptr;
    std::vector<void *> ipc_opened;
    std::string halo_mode = "none";
-   bool nccl_warm = false;
    int launches_per_cycle = 5;
    int k1_grid = 0, k3_grid = 0;   // persistent grids: SMs x resident blocks (capped by the work)
 };
@@ -1168,36 +1167,14 @@ static int enqueue_cycle(lulesh_b200 *h, cudaEvent_t *tl)
    return 0;
 }
 
-// NCCL sets up its connections lazily, at the first operation between two ranks -- allocations
-// and IPC traffic that are illegal under stream capture.  One eager pass over the three exchange
-// patterns of a cycle (all of them write scratch only: gnewdt, fhalo receive slots, ghost slots)
-// leaves nothing to set up when the cycle is captured.
-static int warm_nccl(lulesh_b200 *h)
-{
-   int rc;
-   cudaStream_t cs = h->comm_stream;
-   CK(cudaStreamSynchronize(h->stream));
-   NK(h->nccl->AllReduce(&h->P.ctl->gnewdt, &h->P.ctl->gnewdt, 1, ncclDouble, ncclMin, h->comm, cs));
-   if ((rc = exchange_nodes(h, cs))) return rc;
-   if ((rc = exchange_monoq(h, cs))) return rc;
-   CK(cudaStreamSynchronize(cs));
-   h->launches -= 2;
-   h->nccl_warm = true;
-   return 0;
-}
-
 static int ensure_graph(lulesh_b200 *h)
 {
    if (h->graph && h->graph_debug == h->debug) return 0;
    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
-   const bool nccl_cycle = h->numRanks > 1 && !h->p2p;
-   int rc;
-   if (nccl_cycle && !h->nccl_warm && (rc = warm_nccl(h))) return rc;
    cudaGraph_t g;
    const int64_t saved = h->launches;
-   // NCCL's enqueue path may touch the CUDA API from its own helper thread
-   CK(cudaStreamBeginCapture(h->stream, nccl_cycle ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
-   rc = enqueue_cycle(h, nullptr);
+   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+   int rc = enqueue_cycle(h, nullptr);
    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
    h->launches_per_cycle = (int)(h->launches - saved);
    h->launches = saved;
@@ -1213,14 +1190,13 @@ static bool use_graph(const lulesh_b200 *h)
 {
    // A cycle is captured once and replayed: 5 kernels at one rank; kernels + peer-to-peer exchange
    // kernels on two streams at several ranks.  The NCCL fallback launches its cycles eagerly:
-   // capturing ncclSend/ncclRecv/ncclAllReduce on the forked stream (after an eager warm-up pass,
-   // warm_nccl) is implemented but failed on the 2-GPU box in round 2 as it had in round 1, so it
-   // is opt-in (LULESH_B200_NCCL_GRAPH=1).  LULESH_B200_NO_GRAPH=1 launches every cycle eagerly.
+   // a captured cycle with ncclAllReduce / ncclSend / ncclRecv on the forked stream reported an
+   // NCCL internal error in round 1 and, with an eager warm-up pass and relaxed capture mode,
+   // dead-locked in round 2 (NCCL 2.27.3 and 2.28.9, threads and separate processes, with and
+   // without NCCL_GRAPH_REGISTER).  LULESH_B200_NO_GRAPH=1 launches every cycle eagerly.
    static const bool disabled = getenv("LULESH_B200_NO_GRAPH") != nullptr;
-   static const char *ng = getenv("LULESH_B200_NCCL_GRAPH");
-   static const bool nccl_graph = ng && ng[0] == '1';
    if (disabled) return false;
-   return h->numRanks == 1 || h->p2p || nccl_graph;
+   return h->numRanks == 1 || h->p2p;
 }
 
 static int enqueue_cycles(lulesh_b200 *h, int n)
