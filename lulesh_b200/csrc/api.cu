@@ -1,7 +1,8 @@
 // C ABI + runtime of the B200-native Lagrange-leapfrog step: device mirror of
 // the reference Domain (lulesh.h:148-595) in HBM, the per-cycle launch sequence
-// (CUDA graph at one rank; compute + comm streams with NCCL halo exchange at
-// several ranks) and the host-side construction of the device layouts.
+// (one CUDA graph per cycle; at several ranks a compute and a communication stream
+// with peer-to-peer stores over NVLink or, as fallback, NCCL send/recv + allreduce)
+// and the host-side construction of the device layouts.
 //
 // There is no CPU fallback anywhere in this file: without a usable sm_100
 // device every compute entry point returns LULESH_B200_ECUDA.

@@ -2,6 +2,9 @@
 //
 // One cycle = K6 time_increment -> K1 force_elem -> K2 node_update ->
 //             K3 kinematics_grad -> K45 material (monoq + EOS + dt minima).
+// Several ranks: K6 with its min-reduction, the shared-node chain (k_node_boundary_*,
+// k_peer_pack/wait) and the MonoQ exchange + the face-layer part of K45 run on a second,
+// high-priority stream underneath K1, K2 and the interior part of K45 (api.cu: enqueue_cycle).
 // All index arrays (nodelist, face neighbours, region work list, corner gather
 // table) are READ FROM MEMORY; nothing is synthesised from (i,j,k).
 //
