@@ -24,6 +24,7 @@ are the config-3-size records (16.8 M elements, ~16 GB, 6 s per cycle on 6 cores
 
     OMP_NUM_THREADS=6 oracle/_ref/lulesh_omp -s 256 -i 10 -r 1 -c 0 > /tmp/gold/s256_i10.out
     OMP_NUM_THREADS=6 oracle/_ref/lulesh_omp -s 256 -i 40 -r 1 -c 0 > /tmp/gold/s256_i40.out
+    OMP_NUM_THREADS=8 oracle/_ref/lulesh_omp -s 384 -i 10 -r 1 -c 0 > /tmp/gold/s384_i10.out   # config 4's mesh, 42 GB
 """
 import io, json, os, subprocess, sys
 import numpy as np
@@ -110,7 +111,7 @@ def main():
                     rec = json.loads(line[len("REFJSON "):])
                     rec.pop("elapsed", None)
                     gold[f"lulesh_omp -s {rec['nx']} -r 1 -c 0"] = rec
-    for tag in ("s256_i10", "s256_i40"):
+    for tag in ("s256_i10", "s256_i40", "s384_i10"):
         p = f"/tmp/gold/{tag}.out"
         if os.path.exists(p):
             for line in open(p):

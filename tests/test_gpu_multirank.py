@@ -210,3 +210,40 @@ def test_error_on_one_rank_stops_every_rank(lb, halo, monkeypatch):
     assert [c for c, _, _ in res] == [lb.VOLUME_ERROR, lb.VOLUME_ERROR], res
     assert res[0][1] == res[1][1] and 20 <= res[0][1] <= 22, res     # same cycle on both ranks
     assert max(t for _, _, t in res) < 3.0, res                        # no 4 s spin time-outs
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_config4_strong_scaling_layouts_against_reference(lb, goldens, n):
+    """BASELINE config 4 at its real size: the global 384^3 mesh on 1x1x2 (384x384x192 per GPU), 1x2x2
+    and 2x2x2 ranks against the reference's single-domain `-s 384 -i 10` run -- the oracle SURVEY 8(d)
+    names for the 2- and 4-rank layouts the reference cannot run itself.  Device-side setup."""
+    if ngpu() < n:
+        pytest.skip(f"needs {n} GPUs")
+    gold = goldens["lulesh_omp -s 384 -i 10 -r 1 -c 0"]
+    decomp = lb.decompose(n)
+    sizes = tuple(384 // p for p in decomp)
+    uid = lb.get_unique_id()
+    out, errs = [None] * n, []
+
+    def body(r):
+        try:
+            dev = lb.Device.sedov(sizes[0], num_ranks=n, rank=r, decomp=decomp, sizes=sizes, device=r, unique_id=uid)
+            dev.sum_nodal_mass()
+            dev.run(10)
+            s = dev.scalars
+            e = dev.download("e")
+            out[r] = (s.cycle, s.time, s.deltatime, float(e[0]), float(np.sum(e)), float(np.sum(dev.download("p"))))
+            dev.close()
+        except Exception as ex:   # pragma: no cover
+            errs.append(ex)
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    assert all(o[:3] == out[0][:3] for o in out)                      # time controls bit-identical on all ranks
+    assert out[0][0] == gold["cycles"] == 10
+    assert abs(out[0][1] - gold["time"]) <= 1e-12 * gold["time"]
+    assert abs(out[0][3] - gold["e0"]) <= 1e-8 * gold["e0"]            # origin element lives on rank 0
+    assert abs(sum(o[4] for o in out) - gold["sum_e"]) <= 1e-9 * gold["sum_e"]
+    assert abs(sum(o[5] for o in out) - gold["sum_p"]) <= 1e-9 * gold["sum_p"]

@@ -177,6 +177,25 @@ def test_config3_at_full_size_against_reference(lb, goldens, its):
     dev.close()
 
 
+def test_config4_mesh_at_full_size_against_reference(lb, goldens):
+    """BASELINE config 4's mesh on one GPU: 384^3 = 56.6 M elements (31 GB of HBM) against the
+    reference's own `-s 384 -i 10` run (42 GB and 25 s per cycle on the 8 cores of the build
+    container; tests/golden/make_goldens.py).  Device-side setup."""
+    gold = goldens["lulesh_omp -s 384 -i 10 -r 1 -c 0"]
+    dev = lb.Device.sedov(384)
+    dev.run(10)
+    s = dev.scalars
+    assert s.cycle == gold["cycles"] == 10
+    assert abs(s.time - gold["time"]) <= 1e-12 * gold["time"]
+    assert abs(s.deltatime - gold["dt"]) <= 1e-10 * gold["dt"]
+    e = dev.download("e")
+    assert abs(e[0] - gold["e0"]) / gold["e0"] <= 1e-8
+    for name, key in (("e", "sum_e"), ("p", "sum_p"), ("q", "sum_q"), ("v", "sum_v"), ("ss", "sum_ss")):
+        got = seqsum(e if name == "e" else dev.download(name))
+        assert abs(got - gold[key]) <= 1e-9 * abs(gold[key]) + 1e-12, name
+    dev.close()
+
+
 def test_region_flags_do_not_change_the_answer(lb):
     """-r/-b/-c only change how much EOS work is done.  On the device the
     per-element arithmetic is identical, so the results are bit-identical."""
