@@ -292,3 +292,19 @@ def test_viz_dump_holds_the_reference_field_set(lb, tmp_path):
     assert np.allclose(vtk["speed"], speed, rtol=1e-15)
     with pytest.raises(OSError):
         dom.write_vtk(tmp_path / "missing_dir" / "x.vtk")
+
+
+def test_reference_binding_view_against_reference_domain():
+    """include/lulesh_b200_reference_binding.h on the CPU: the view it builds from the REFERENCE's own
+    Domain (oracle/_ref/binding_check, compiled from /root/reference by oracle/Makefile) points at the
+    reference's arrays, and the node -> corner lists it rebuilds from nodelist equal the ones the
+    reference builds itself when threaded (lulesh-init.cc:272-337).  No GPU call is made."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "binding_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/binding_check was not built (needs /root/reference at build time)")
+    for args, entries in ((["6"], 8 * 6 ** 3), (["9", "16", "1", "8"], 8 * 9 ** 3)):
+        p = subprocess.run([exe] + args, capture_output=True, text=True, timeout=120,
+                           env=dict(os.environ, OMP_NUM_THREADS="2"))
+        assert p.returncode == 0, p.stdout + p.stderr
+        assert f"corner_entries_compared={entries}" in p.stdout, p.stdout
